@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec, forward+backward, BASELINE.json cfg 3 (1M Gaussians, 1920x1080, orbit views).
+
+A "step" is one camera view through the hot path: plugin render (attribute activations + rasterizer forward)
+-> loss on colour + depth + opacity -> backward -> depth->normal map.  One process per GPU (torchrun for N>1),
+views sharded k ≡ rank (mod N), Gaussian-parameter gradients stay local, one all_gather of the per-view loss
+scalars at the end of the timed region ("weak" scaling: every rank does K steps).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference --gpus N ...            # the UNMODIFIED reference CUDA extension
+                                                           # (oracle/_ref/_refC.so) driven by the same loop
+
+Prints ONE JSON line on rank 0 (see DESIGN.md §Measurement for every key).
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+STAGES = ["preprocess_fwd", "tile_scan", "scatter", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd",
+          "depth2normal"]
+KERNELS_PER_STEP = 9  # init_header, preprocess_fwd, tile_scan, scatter, tile_sort, render_fwd, render_bwd,
+#                        preprocess_bwd, depth2normal (+ the pixel-loss kernels are torch's, not counted)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="new", choices=["new", "reference"])
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--gaussians", type=int, default=None, help="override P (debug only; invalidates the number)")
+    ap.add_argument("--pipelined", type=int, default=1, help="sync-free forward (capacity from high-water mark)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.p = gpu_index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                      text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class HostCamera:
+    """Per-view camera whose matrices live in PINNED host memory; `.upload(dev)` is the step's H2D copy."""
+
+    def __init__(self, cam):
+        self.FoVx, self.FoVy = cam.FoVx, cam.FoVy
+        self.image_width, self.image_height = cam.image_width, cam.image_height
+        self.h_view = cam.world_view_transform.contiguous().pin_memory()
+        self.h_proj = cam.full_proj_transform.contiguous().pin_memory()
+        self.h_pos = cam.camera_center.contiguous().pin_memory()
+        K = cam.intrinsics
+        self.fx, self.fy, self.cx, self.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+        self.K = K
+        self.nbytes = (self.h_view.numel() + self.h_proj.numel() + self.h_pos.numel()) * 4
+
+    def upload(self, dev):
+        self.world_view_transform = self.h_view.to(dev, non_blocking=True)
+        self.full_proj_transform = self.h_proj.to(dev, non_blocking=True)
+        self.camera_center = self.h_pos.to(dev, non_blocking=True)
+        return self
+
+
+def make_step(impl, model, dev, H, W):
+    """Returns step(cam) -> scalar loss tensor (on device).  Same loop for both arms; only the rasterizer and the
+    depth->normal op differ (reference: its CUDA extension + its torch depth2normal)."""
+    from gaustudio_b200 import ops, renderers
+    g = torch.Generator().manual_seed(1234)
+    tc = torch.rand(3, H, W, generator=g).to(dev)
+    td = 3.0 * torch.rand(1, H, W, generator=g).to(dev)
+    to = torch.rand(1, H, W, generator=g).to(dev)
+    params = model.parameters_list()
+
+    if impl == "new":
+        renderer = renderers.make({"name": "vanilla_renderer"})
+
+        def render(cam):
+            return renderer.render(cam, model)
+
+        def normal(cam, depth):
+            return ops.depth2normal(depth, cam.fx, cam.fy, cam.cx, cam.cy)
+    else:
+        from gaustudio_b200.rasterizer import GaussianRasterizationSettings
+        from gaustudio_b200.renderers.vanilla_renderer import VanillaRenderer
+        from oracle import ref_driver, ref_torch_ops
+        props = VanillaRenderer({})
+        bg = torch.zeros(3, device=dev)  # the reference dereferences bg on the device in backward (backward.cu:586)
+
+        def render(cam):
+            xyz, shs, colors, opacity, scales, rotations, cov = props.get_gaussians_properties(cam, model)
+            m2d = torch.zeros_like(xyz, requires_grad=True) + 0
+            rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, math.tan(cam.FoVx * 0.5),
+                                               math.tan(cam.FoVy * 0.5), bg, 1.0, cam.world_view_transform,
+                                               cam.full_proj_transform, model.active_sh_degree, cam.camera_center, False,
+                                               False)
+            color, radii, depth, median, opac = ref_driver.rasterize(rs, xyz, m2d, opacity, shs=shs, scales=scales,
+                                                                     rotations=rotations)
+            return {"render": color, "rendered_depth": depth, "rendered_final_opacity": opac, "radii": radii}
+
+        def normal(cam, depth):
+            return ref_torch_ops.depth2normal(depth, cam.K)
+
+    def step(cam):
+        for p in params:
+            p.grad = None
+        out = render(cam)
+        loss = (out["render"] - tc).abs().mean() + 0.1 * (out["rendered_depth"] - td).abs().mean() + \
+            0.1 * (out["rendered_final_opacity"] - to).abs().mean()
+        loss.backward()
+        n = normal(cam, out["rendered_depth"].detach()[0])
+        return loss.detach() + 0.0 * n[0, 0, 0]
+
+    return step
+
+
+def algorithmic_bytes(P, P_vis, D, R, R_need, W, H):
+    """SURVEY.md §8(d) per-view algorithmic bytes of each stage group."""
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    return {
+        "preprocess_fwd": P * (44 + 12 * (D + 1) ** 2) + P_vis * 48,
+        "binning": R * 44,
+        "render_fwd": R_need * 44 + W * H * 40 + T * 8,
+        "render_bwd": R_need * 44 + W * H * 40 + R_need * 40,
+        "preprocess_bwd": P_vis * (300 + 304),
+    }
+
+
+def cpu_baseline(model, cam, D):
+    """CPU oracle (C++/OpenMP port of the reference algorithm) on ONE view of the same workload."""
+    import numpy as np
+    from oracle.oracle import Oracle, num_threads
+    with torch.no_grad():
+        x = dict(means3D=model.get_attribute("xyz").cpu().numpy(), opacities=model.get_attribute("opacity").cpu().numpy(),
+                 scales=model.get_attribute("scale").cpu().numpy(), rotations=model.get_attribute("rot").cpu().numpy(),
+                 shs=model.get_features.cpu().numpy(), viewmatrix=cam.h_view.numpy(), projmatrix=cam.h_proj.numpy(),
+                 campos=cam.h_pos.numpy(), tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+                 W=cam.image_width, H=cam.image_height, sh_degree=D)
+    o = Oracle()
+    H, W = cam.image_height, cam.image_width
+    ones = np.ones((3, H, W), np.float32)
+    t0 = time.time()
+    n = 0
+    while True:
+        o.forward(**x)
+        o.backward(ones, ones[0], None, ones[0])
+        n += 1
+        if time.time() - t0 > 8.0 or n >= 4:
+            break
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "views/s", "cores": num_threads(), "kind": "port",
+            "sample": f"{n} view(s) of the same workload, fwd+bwd, CPU oracle (oracle/gsr_oracle.cpp, OpenMP)"}
+
+
+def main():
+    a = parse()
+    from gaustudio_b200 import _C, _lib, parallel
+    from gaustudio_b200.synthetic import CONFIGS, build_config
+    if a.impl == "reference":
+        # the reference has no multi-GPU path: rank 0 alone runs it, the other ranks exit without work
+        rank, local_rank, world = parallel.env_world()
+        if rank != 0:
+            return 0
+        world = 1
+    else:
+        rank, local_rank, world = parallel.init_distributed()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    cfgname = a.config
+    nviews_total = CONFIGS[cfgname]["K"] * (4 if world > 1 and cfgname == "cfg3" else 1)  # cfg4 = 800 views
+    model, _, c = build_config(cfgname, P=a.gaussians, K=1)
+    from gaustudio_b200.camera import orbit_cameras
+    K, Wn = a.steps, a.warmup
+    my_views = [(rank + world * i) % nviews_total for i in range(K + Wn)]
+    cams = orbit_cameras(nviews_total, c["radius"], c["elev"], c["W"], c["H"], c["fovx"], c["fovy"], indices=my_views)
+    hcams = [HostCamera(cm) for cm in cams]
+    model.to(dev).requires_grad_(True)
+    D = model.active_sh_degree
+    H, W, P = c["H"], c["W"], c["P"]
+    step = make_step(a.impl, model, dev, H, W)
+    if a.impl == "new":
+        _C.set_pipelined(bool(a.pipelined))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1 and a.impl == "new":
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---------------- warm-up (W >= 3) ----------------
+    for i in range(Wn):
+        step(hcams[i].upload(dev))
+    sync_all()
+
+    # ---------------- leg 1: device-resident inputs ("value") ----------------
+    for hc in hcams:
+        hc.upload(dev)  # cameras resident in HBM before the timed region
+    sync_all()
+    L = _lib.lib()
+    if a.impl == "new":
+        L.gsr_profile_enable(1)
+        ms0 = (ctypes.c_float * 8)(); cn0 = (ctypes.c_int * 8)()
+        L.gsr_profile_read(ms0, cn0)  # drop warm-up records
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    losses = torch.zeros(K, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        losses[i] = step(hcams[Wn + i])
+    if a.impl == "new":
+        all_losses = parallel.gather_view_losses(losses, K * world, rank, world)  # the one collective
+    e1.record()
+    sync_all()
+    ms_dev = parallel.barrier_max_ms(e0.elapsed_time(e1), dev) if a.impl == "new" else e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    stage_ms = None
+    if a.impl == "new":
+        ms = (ctypes.c_float * 8)(); cn = (ctypes.c_int * 8)()
+        L.gsr_profile_read(ms, cn)
+        L.gsr_profile_enable(0)
+        stage_ms = {STAGES[i]: (ms[i] / cn[i] if cn[i] else 0.0) for i in range(8)}
+        _C.check_pipeline(wait=True)
+
+    # ---------------- leg 2: end to end through the public API with host buffers ("e2e") ----------------
+    host_loss = torch.empty(1).pin_memory()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(K):
+        hc = hcams[Wn + i].upload(dev)               # H2D of this step's inputs from pinned memory
+        host_loss.copy_(step(hc).reshape(1))         # D2H read of the step's result
+    e3.record()
+    sync_all()
+    ms_e2e = parallel.barrier_max_ms(e2.elapsed_time(e3), dev) if a.impl == "new" else e2.elapsed_time(e3)
+    if a.impl == "new":
+        _C.check_pipeline(wait=True)
+
+    if rank != 0:
+        return 0
+
+    # ---------------- workload statistics for the roofline (outside the timed regions) ----------------
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    roof, stages_out = None, None
+    if a.impl == "new":
+        _C.set_pipelined(False)
+        stats = []
+        from gaustudio_b200.renderers.vanilla_renderer import VanillaRenderer
+        props = VanillaRenderer({})
+        with torch.no_grad():
+            for hc in hcams[Wn:Wn + min(K, 4)]:
+                xyz, shs, _, opacity, scales, rotations, _ = props.get_gaussians_properties(hc, model)
+                e = torch.Tensor([])
+                R, *_o, radii, gb, bb, ib = _C.rasterize_gaussians(
+                    torch.zeros(3, device=dev), xyz, e, opacity, scales, rotations, 1.0, e, hc.world_view_transform,
+                    hc.full_proj_transform, math.tan(hc.FoVx * 0.5), math.tan(hc.FoVy * 0.5), H, W, shs.contiguous(), D,
+                    hc.camera_center, False, False)
+                ex = _C.debug_export(P, W, H, R, gb, bb, ib)
+                nc = ex["n_contrib"]
+                Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+                pad = torch.zeros(Hp, Wp, dtype=nc.dtype, device=dev)
+                pad[:H, :W] = nc
+                r_need = int(pad.view(Hp // 16, 16, Wp // 16, 16).amax(dim=(1, 3)).sum())
+                stats.append((R, r_need, int((radii > 0).sum())))
+        R = sum(s[0] for s in stats) / len(stats)
+        R_need = sum(s[1] for s in stats) / len(stats)
+        P_vis = sum(s[2] for s in stats) / len(stats)
+        ab = algorithmic_bytes(P, P_vis, D, R, R_need, W, H)
+        grp_ms = {"preprocess_fwd": stage_ms["preprocess_fwd"],
+                  "binning": stage_ms["tile_scan"] + stage_ms["scatter"] + stage_ms["tile_sort"],
+                  "render_fwd": stage_ms["render_fwd"], "render_bwd": stage_ms["render_bwd"],
+                  "preprocess_bwd": stage_ms["preprocess_bwd"]}
+        stages_out = {}
+        traffic = {}
+        tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tf):
+            traffic = json.load(open(tf))
+        for k in grp_ms:
+            gbs = ab[k] / (grp_ms[k] * 1e-3) / 1e9 if grp_ms[k] > 0 else 0.0
+            stages_out[k] = {"ms": round(grp_ms[k], 4), "algorithmic_MB": round(ab[k] / 1e6, 2), "GBps": round(gbs, 1),
+                             "frac": round(gbs / hbm_peak, 4)}
+        dom = max(grp_ms, key=lambda k: grp_ms[k])
+        roof = {"kernel": dom, "bound": "hbm", "achieved": stages_out[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": stages_out[dom]["frac"], "traffic": traffic.get(dom), "peak_source": peak_src,
+                "note": "FP32/SFU-bound compositing: HBM fraction is low by construction (DESIGN.md §Roofline)"}
+        stages_out["_workload"] = {"R": R, "R_need": R_need, "P_visible": P_vis,
+                                   "depth2normal_ms": round(stage_ms["depth2normal"], 4)}
+
+    out = {
+        "metric": "views/sec fwd+bwd @1M Gaussians/1080p" if cfgname == "cfg3" and a.gaussians is None else
+                  f"views/sec fwd+bwd ({cfgname})",
+        "value": world * K / (ms_dev * 1e-3) if a.impl == "new" else K / (ms_dev * 1e-3),
+        "unit": "views/s", "n_gpus": a.gpus if a.impl == "new" else 1, "steps": K, "warmup": Wn,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfgname}: {P} Gaussians (ball rho={c.get('rho')}, s0={c.get('s0')}, seed {c['seed']}), "
+                               f"{W}x{H}, SH degree {D}, orbit views r={c['radius']} elev={c['elev']}, "
+                               "fwd+bwd (L1 colour + 0.1 L1 depth + 0.1 L1 opacity) + depth->normal",
+                   "views_total": nviews_total, "parallelism": f"view-sharded x{world}",
+                   "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 66 MB of per-view outputs vs 126 MB)",
+                   "forward_mode": "pipelined (no host sync; overflow-checked)" if a.pipelined and a.impl == "new" else
+                                   "exact (one blocking 8-byte D2H per view, like the reference)"},
+        "clocks": clocks,
+        "e2e": {"value": (world if a.impl == "new" else 1) * K / (ms_e2e * 1e-3), "unit": "views/s",
+                "h2d_bytes_per_step": hcams[0].nbytes if a.impl == "new" else 0,
+                "d2h_bytes_per_step": 4 if a.impl == "new" else 0, "ms_per_step": ms_e2e / K},
+        "gpu_launches": KERNELS_PER_STEP * K * 2 if a.impl == "new" else 0,
+    }
+    if a.impl == "new":
+        out["roofline"] = roof
+        out["stages"] = stages_out
+        if not a.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(model, hcams[Wn], D)
+            except Exception as ex:  # noqa: BLE001
+                out["cpu_baseline"] = {"error": str(ex)}
+    else:
+        out["impl"] = "reference"
+        out["e2e"]["value"] = K / (ms_e2e * 1e-3)
+        out["cpu_baseline"] = {"value": out["e2e"]["value"], "unit": "views/s", "cores": 1, "kind": "reference",
+                               "sample": "the reference has no CPU implementation of this path: its own CUDA "
+                                         "extension (unmodified sources, sm_100a) driven by one host thread"}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,214 @@
+"""Python mirror of the reference's pybind11 module `_C`
+($RAST/ext.cpp:15-19, $RAST/rasterize_points.cu:35-231): same three functions, same argument order, same
+returned tuples -- implemented on top of the C ABI of libgsr_b200.so (include/gsr.h) through ctypes.
+PyTorch is only the owner of device memory and of the current stream here.
+"""
+import ctypes as C
+import threading
+
+import torch
+
+from . import _lib
+
+# Pipelined (sync-free) forward: opt-in.  In exact mode (default) the forward does one blocking 8-byte
+# device->host read of num_rendered to size the binning buffer, like the reference (rasterizer_impl.cu:284).
+# In pipelined mode the binning buffer is sized from the high-water mark of earlier views with the same
+# (device, P, W, H) and the count is read asynchronously; an overflow is reported by `check_pipeline()` /
+# the next forward (async-error semantics, like CUDA errors without `debug` in the reference).
+_pipeline = threading.local()
+
+
+def set_pipelined(enabled, slack=1.5):
+    _pipeline.enabled = bool(enabled)
+    _pipeline.slack = float(slack)
+    _pipeline.hw = {}
+    _pipeline.pending = []
+
+
+def _pl():
+    if not hasattr(_pipeline, "enabled"):
+        set_pipelined(False)
+    return _pipeline
+
+
+def check_pipeline(wait=False):
+    """Raise if a pipelined forward overflowed its binning capacity.  wait=True drains all pending views."""
+    pl = _pl()
+    keep = []
+    for host, ev, cap, key in pl.pending:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            r = int(host.item())
+            pl.hw[key] = max(pl.hw.get(key, 0), int(r * pl.slack) + 4096)
+            if r > cap:
+                pl.pending = []
+                raise RuntimeError(f"gsr: pipelined forward overflowed its binning capacity ({r} > {cap}); "
+                                   "that view's outputs are incomplete -- re-run it")
+        else:
+            keep.append((host, ev, cap, key))
+    pl.pending = keep
+
+
+def _ptr(t):
+    """Device pointer of a contiguous float32/int32/uint8 tensor; None for an empty (absent) tensor."""
+    if t is None or t.numel() == 0:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t, device, name):
+    if t is None or t.numel() == 0:
+        return t
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32")
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous()
+
+
+class _Arena:
+    """The three resizable byte tensors of rasterize_points.cu:27-33,74-81."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = torch.empty(0, dtype=torch.uint8, device=device)
+        self.fn = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.buf.data_ptr()
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                        prefiltered, debug):
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    if not means3D.is_cuda:
+        raise RuntimeError("gaustudio_b200 runs on CUDA (sm_100a) only; means3D must be a CUDA tensor")
+    L = _lib.lib()
+    dev = means3D.device
+    P, H, W = means3D.size(0), int(image_height), int(image_width)
+    fopt = dict(dtype=torch.float32, device=dev)
+    if P == 0:  # rasterize_points.cu:84
+        e = torch.empty(0, dtype=torch.uint8, device=dev)
+        return (0, torch.zeros(3, H, W, **fopt), torch.zeros(1, H, W, **fopt), torch.zeros(3, H, W, **fopt),
+                torch.zeros(1, H, W, **fopt), torch.zeros(0, dtype=torch.int32, device=dev), e, e.clone(), e.clone())
+    means3D = _f32(means3D, dev, "means3D"); colors = _f32(colors, dev, "colors_precomp")
+    opacity = _f32(opacity, dev, "opacities"); scales = _f32(scales, dev, "scales")
+    rotations = _f32(rotations, dev, "rotations"); cov3D_precomp = _f32(cov3D_precomp, dev, "cov3D_precomp")
+    viewmatrix = _f32(viewmatrix, dev, "viewmatrix"); projmatrix = _f32(projmatrix, dev, "projmatrix")
+    sh = _f32(sh, dev, "shs"); campos = _f32(campos, dev, "campos")
+    background = _f32(background, dev, "bg")  # gaustudio passes a CPU tensor (vanilla_renderer.py:23)
+    M = sh.size(1) if sh.numel() != 0 else 0  # rasterize_points.cu:86-90
+
+    out_color = torch.empty(3, H, W, **fopt); out_depth = torch.empty(1, H, W, **fopt)
+    out_median = torch.empty(3, H, W, **fopt); out_opacity = torch.empty(1, H, W, **fopt)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+
+    pl = _pl()
+    cap, host = 0, None
+    key = (dev.index, P, W, H)
+    if pl.enabled:
+        check_pipeline()
+        cap = pl.hw.get(key, 0)
+        host = torch.empty(1, dtype=torch.int64).pin_memory()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        r = L.gsr_forward(geom.fn, None, binning.fn, None, img.fn, None, P, int(degree), M, _ptr(background), W, H,
+                          _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales), float(scale_modifier),
+                          _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                          float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), _ptr(out_color), _ptr(out_depth),
+                          _ptr(out_median), _ptr(out_opacity), _ptr(radii), int(bool(debug)), int(cap),
+                          C.c_void_p(host.data_ptr()) if host is not None else None, C.c_void_p(stream.cuda_stream))
+        if r < 0:
+            raise RuntimeError("gsr_forward failed: " + _lib.last_error())
+        if pl.enabled:
+            if cap > 0:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                pl.pending.append((host, ev, cap, key))
+            else:  # first view of this shape ran in exact mode: seed the high-water mark
+                pl.hw[key] = int(r * pl.slack) + 4096
+    return int(r), out_color, out_depth, out_median, out_opacity, radii, geom.buf, binning.buf, img.buf
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                                 viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth,
+                                 dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, debug):
+    L = _lib.lib()
+    dev = means3D.device
+    P = means3D.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    M = sh.size(1) if sh.numel() != 0 else 0
+    fopt = dict(dtype=torch.float32, device=dev)
+    alloc = torch.zeros if P == 0 else torch.empty  # every element is written by the kernels when P > 0
+    dL_dmeans3D = alloc(P, 3, **fopt); dL_dmeans2D = alloc(P, 3, **fopt); dL_dcolors = alloc(P, 3, **fopt)
+    dL_dopacity = alloc(P, 1, **fopt); dL_dcov3D = alloc(P, 6, **fopt); dL_dsh = alloc(P, M, 3, **fopt)
+    dL_dscales = alloc(P, 3, **fopt); dL_drotations = alloc(P, 4, **fopt)
+    if P != 0:
+        means3D = _f32(means3D, dev, "means3D"); colors = _f32(colors, dev, "colors_precomp")
+        scales = _f32(scales, dev, "scales"); rotations = _f32(rotations, dev, "rotations")
+        cov3D_precomp = _f32(cov3D_precomp, dev, "cov3D_precomp"); viewmatrix = _f32(viewmatrix, dev, "viewmatrix")
+        projmatrix = _f32(projmatrix, dev, "projmatrix"); sh = _f32(sh, dev, "shs"); campos = _f32(campos, dev, "campos")
+        background = _f32(background, dev, "bg")
+        gc = _f32(dL_dout_color, dev, "dL_dout_color"); gd = _f32(dL_dout_depth, dev, "dL_dout_depth")
+        gm = _f32(dL_dout_median_depth, dev, "dL_dout_median_depth")
+        go = _f32(dL_dout_final_opacity, dev, "dL_dout_final_opacity")
+        radii = radii.contiguous()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = L.gsr_backward(P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh),
+                                _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                                _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx),
+                                float(tan_fovy), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer),
+                                _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(gm), _ptr(go), _ptr(dL_dmeans2D), None,
+                                _ptr(dL_dopacity), _ptr(dL_dcolors), None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
+                                _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), int(bool(debug)),
+                                C.c_void_p(stream.cuda_stream))
+        if rc < 0:
+            raise RuntimeError("gsr_backward failed: " + _lib.last_error())
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    L = _lib.lib()
+    dev = means3D.device
+    P = means3D.size(0)
+    present = torch.zeros(P, dtype=torch.bool, device=dev)
+    if P != 0:
+        means3D = _f32(means3D, dev, "means3D")
+        viewmatrix = _f32(viewmatrix, dev, "viewmatrix"); projmatrix = _f32(projmatrix, dev, "projmatrix")
+        with torch.cuda.device(dev):
+            rc = L.gsr_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix), C.c_void_p(present.data_ptr()),
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if rc < 0:
+            raise RuntimeError("gsr_mark_visible failed: " + _lib.last_error())
+    return present
+
+
+def debug_export(P, W, H, R, geomBuffer, binningBuffer, imageBuffer):
+    """Internal state of a forward as named tensors (parity tests; see gsr_debug_export in include/gsr.h)."""
+    L = _lib.lib()
+    dev = geomBuffer.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    o = dict(point_list=torch.zeros(R, dtype=torch.int32, device=dev),
+             ranges=torch.zeros(T, 2, dtype=torch.int32, device=dev),
+             n_contrib=torch.zeros(H, W, dtype=torch.int32, device=dev),
+             final_T=torch.zeros(H, W, device=dev), means2D=torch.zeros(P, 2, device=dev),
+             conic_opacity=torch.zeros(P, 4, device=dev), depths=torch.zeros(P, device=dev),
+             rgb=torch.zeros(P, 3, device=dev), cov3D=torch.zeros(P, 6, device=dev),
+             tiles_touched=torch.zeros(P, dtype=torch.int32, device=dev),
+             clamped=torch.zeros(P, 3, dtype=torch.uint8, device=dev))
+    with torch.cuda.device(dev):
+        rc = L.gsr_debug_export(P, W, H, int(R), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                                _ptr(o["point_list"]), _ptr(o["ranges"]), _ptr(o["n_contrib"]), _ptr(o["final_T"]),
+                                _ptr(o["means2D"]), _ptr(o["conic_opacity"]), _ptr(o["depths"]), _ptr(o["rgb"]),
+                                _ptr(o["cov3D"]), _ptr(o["tiles_touched"]), _ptr(o["clamped"]),
+                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc < 0:
+        raise RuntimeError("gsr_debug_export failed: " + _lib.last_error())
+    return o

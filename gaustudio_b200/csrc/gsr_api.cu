@@ -1,0 +1,370 @@
+// C ABI of libgsr_b200 (include/gsr.h): buffer carving, stage orchestration, error reporting.
+// Orchestration restates CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// ($RAST/cuda_rasterizer/rasterizer_impl.cu:141-153, 198-343, 347-452) on top of the B200 kernels.
+#include "../../include/gsr.h"
+#include "gsr_internal.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace gsr {
+
+namespace {
+thread_local std::string g_err;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T> inline void take(char*& p, T*& out, size_t count) {
+  p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p), 256));
+  out = reinterpret_cast<T*>(p);
+  p += count * sizeof(T);
+}
+
+bool check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+// CHECK_CUDA of the reference (auxiliary.h:166-173): with debug, synchronise and surface errors per stage
+bool stage_ok(bool debug, cudaStream_t st, const char* what) {
+  if (!check(cudaGetLastError(), what)) return false;
+  if (debug && !check(cudaStreamSynchronize(st), what)) return false;
+  return true;
+}
+
+// ---- optional per-stage timing (gsr_profile_*) ----
+struct ProfRec { int stage; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+struct Prof {
+  int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  Prof(int s, cudaStream_t t) : stage(s), st(t) {
+    if (!g_prof_on) return;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+  }
+  ~Prof() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    g_prof.push_back({stage, a, b});
+  }
+};
+}  // namespace
+
+GeomView carve_geom(char* base, int P) {
+  GeomView g;
+  char* p = base;
+  take(p, g.splat, (size_t)P * SPLAT_F4);
+  take(p, g.rect, (size_t)P);
+  take(p, g.cov3D, (size_t)P * 6);
+  take(p, g.clamped, (size_t)P);
+  take(p, g.radii, (size_t)P);
+  take(p, g.tiles_touched, (size_t)P);
+  take(p, g.grad, (size_t)P * GRAD_F);
+  return g;
+}
+size_t geom_bytes(int P) {
+  GeomView g = carve_geom(nullptr, P);
+  return reinterpret_cast<size_t>(g.grad + (size_t)P * GRAD_F) + 512;
+}
+ImageView carve_image(char* base, int W, int H) {
+  ImageView im;
+  char* p = base;
+  const size_t N = (size_t)W * H;
+  const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  take(p, im.hdr, 1);
+  take(p, im.final_T, N);
+  take(p, im.n_contrib, N);
+  take(p, im.tile_count, T);
+  take(p, im.tile_range, T);
+  take(p, im.tile_cursor, T);
+  take(p, im.tile_maxc, T);
+  return im;
+}
+size_t image_bytes(int W, int H) {
+  ImageView im = carve_image(nullptr, W, H);
+  const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  return reinterpret_cast<size_t>(im.tile_maxc + T) + 512;
+}
+BinView carve_binning(char* base, long long cap) {
+  BinView b;
+  char* p = base;
+  take(p, b.ents, (size_t)cap);
+  take(p, b.slab, (size_t)cap * SPLAT_F4);
+  return b;
+}
+size_t binning_bytes(long long R) {
+  BinView b = carve_binning(nullptr, R);
+  return reinterpret_cast<size_t>(b.slab + (size_t)R * SPLAT_F4) + 512;
+}
+
+namespace {
+inline char* aligned_base(char* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p), 256)); }
+
+__global__ void k_init_header(ImageHeader* h, unsigned long long cap) {
+  h->num_rendered = 0;
+  h->capacity = cap;
+  h->overflow = 0;
+}
+
+// gaustudio/datasets/__init__.py:106-112,307-380 -- same arithmetic order as the torch ops of the reference:
+//   u' = (u/(W-1))*(W-1);  X = (u'*z)*Kinv00 + z*Kinv02, ...;  n = -normalize(cross(top-bottom, left-right))
+__global__ void k_depth2normal(const float* __restrict__ depth, int W, int H, float ifx, float ify, float ox, float oy,
+                               float dmin, float dmax, const float* __restrict__ rot, float* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+  if (u >= W || v >= H) return;
+  float* o = out + ((size_t)v * W + u) * 3;
+  bool valid = u > 0 && v > 0 && u < W - 1 && v < H - 1;
+  float n0 = -1.f, n1 = -1.f, n2 = -1.f;
+  if (valid) {
+    auto point = [&](int uu, int vv, float& x, float& y, float& z) {
+      z = depth[(size_t)vv * W + uu];
+      const float uz = __fmul_rn(__fmul_rn(__fdiv_rn((float)uu, (float)(W - 1)), (float)(W - 1)), z);
+      const float vz = __fmul_rn(__fmul_rn(__fdiv_rn((float)vv, (float)(H - 1)), (float)(H - 1)), z);
+      x = __fadd_rn(__fmul_rn(uz, ifx), __fmul_rn(z, ox));
+      y = __fadd_rn(__fmul_rn(vz, ify), __fmul_rn(z, oy));
+    };
+    float cx, cy, cz, tx, ty, tz, bx, by, bz, lx, ly, lz, rx, ry, rz;
+    point(u, v, cx, cy, cz); point(u, v - 1, tx, ty, tz); point(u, v + 1, bx, by, bz);
+    point(u - 1, v, lx, ly, lz); point(u + 1, v, rx, ry, rz);
+    auto ok = [&](float z) { return z > dmin && z < dmax; };
+    valid = ok(cz) && ok(tz) && ok(bz) && ok(lz) && ok(rz);
+    if (valid) {
+      const float ax = tx - bx, ay = ty - by, az = tz - bz, hx = lx - rx, hy = ly - ry, hz = lz - rz;
+      float c0 = -(__fmul_rn(ay, hz) - __fmul_rn(az, hy)), c1 = -(__fmul_rn(az, hx) - __fmul_rn(ax, hz)),
+            c2 = -(__fmul_rn(ax, hy) - __fmul_rn(ay, hx));
+      const float len = fmaxf(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e-12f);
+      c0 /= len; c1 /= len; c2 /= len;
+      if (rot) {
+        n0 = c0 * rot[0] + c1 * rot[3] + c2 * rot[6];
+        n1 = c0 * rot[1] + c1 * rot[4] + c2 * rot[7];
+        n2 = c0 * rot[2] + c1 * rot[5] + c2 * rot[8];
+      } else {
+        n0 = c0; n1 = c1; n2 = c2;
+      }
+    }
+  }
+  o[0] = n0; o[1] = n1; o[2] = n2;
+}
+
+__global__ void k_export_geom(int P, GeomView g, float* means2D, float* conic_opacity, float* depths, float* rgb,
+                              float* cov3D, uint32_t* tiles_touched, unsigned char* clamped) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const bool vis = g.radii[i] > 0;
+  float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+  if (vis) { q0 = g.splat[(size_t)i * SPLAT_F4]; q1 = g.splat[(size_t)i * SPLAT_F4 + 1]; q2 = g.splat[(size_t)i * SPLAT_F4 + 2]; }
+  if (means2D) { means2D[2 * i] = q0.x; means2D[2 * i + 1] = q0.y; }
+  if (conic_opacity) { conic_opacity[4 * i] = q0.z; conic_opacity[4 * i + 1] = q0.w; conic_opacity[4 * i + 2] = q1.x; conic_opacity[4 * i + 3] = q1.y; }
+  if (depths) depths[i] = q1.z;
+  if (rgb) { rgb[3 * i] = q1.w; rgb[3 * i + 1] = q2.x; rgb[3 * i + 2] = q2.y; }
+  if (cov3D) for (int k = 0; k < 6; k++) cov3D[6 * i + k] = vis ? g.cov3D[6 * i + k] : 0.f;
+  if (tiles_touched) tiles_touched[i] = g.tiles_touched[i];
+  if (clamped) { const unsigned char c = vis ? g.clamped[i] : 0; clamped[3 * i] = c & 1; clamped[3 * i + 1] = (c >> 1) & 1; clamped[3 * i + 2] = (c >> 2) & 1; }
+}
+__global__ void k_export_list(long long R, BinView b, uint32_t* point_list) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) point_list[i] = (uint32_t)__float_as_int(b.slab[(size_t)i * SPLAT_F4 + 2].z);
+}
+__global__ void k_export_image(int N, int T, ImageView im, uint32_t* ranges, uint32_t* n_contrib, float* final_T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    if (n_contrib) n_contrib[i] = im.n_contrib[i];
+    if (final_T) final_T[i] = im.final_T[i];
+  }
+  if (i < T && ranges) { ranges[2 * i] = im.tile_range[i].x; ranges[2 * i + 1] = im.tile_range[i].y; }
+}
+}  // namespace
+
+void launch_depth2normal(const float* depth, int W, int H, float fx, float fy, float cx, float cy, float dmin,
+                         float dmax, const float* rot, float* out, cudaStream_t st) {
+  dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
+  // K^-1 entries computed on the host in float like torch.inverse of the float32 intrinsics
+  k_depth2normal<<<grd, blk, 0, st>>>(depth, W, H, 1.0f / fx, 1.0f / fy, -cx / fx, -cy / fy, dmin, dmax, rot, out);
+}
+
+void launch_debug_export(int P, int W, int H, long long R, GeomView g, BinView b, ImageView im,
+                         uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib, float* final_T,
+                         float* means2D, float* conic_opacity, float* depths, float* rgb, float* cov3D,
+                         uint32_t* tiles_touched, unsigned char* clamped, cudaStream_t st) {
+  if (P > 0) k_export_geom<<<(P + 255) / 256, 256, 0, st>>>(P, g, means2D, conic_opacity, depths, rgb, cov3D, tiles_touched, clamped);
+  if (R > 0 && point_list) k_export_list<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, b, point_list);
+  const int N = W * H, T = ((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  k_export_image<<<(max(N, T) + 255) / 256, 256, 0, st>>>(N, T, im, ranges, n_contrib, final_T);
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return g_err.c_str(); }
+size_t gsr_geometry_bytes(int P) { return geom_bytes(P); }
+size_t gsr_image_bytes(int width, int height) { return image_bytes(width, height); }
+size_t gsr_binning_bytes(int64_t num_rendered) { return binning_bytes(num_rendered); }
+
+int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc, void* binning_user,
+                    gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background,
+                    int width, int height, const float* means3D, const float* shs, const float* colors_precomp,
+                    const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+                    const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                    const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                    float* out_depth, float* out_median_depth, float* out_opacity, int* radii, int debug,
+                    int64_t r_capacity, int64_t* r_host, void* stream) {
+  (void)background;  // the forward never reads it (no background blend, forward.cu:389-390; quirk 10)
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool dbg = debug != 0;
+  if (P <= 0 || width <= 0 || height <= 0) { g_err = "gsr_forward: P, width and height must be positive"; return -1; }
+  if (colors_precomp == nullptr && shs == nullptr) { g_err = "gsr_forward: need shs or colors_precomp"; return -1; }
+  if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr)) { g_err = "gsr_forward: need scales+rotations or cov3D_precomp"; return -1; }
+  if (D < 0 || D > 3 || (shs && (D + 1) * (D + 1) > M)) { g_err = "gsr_forward: sh degree / coefficient count mismatch"; return -1; }
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y, T = gx * gy;
+  if (gx > 65535 || gy > 65535) { g_err = "gsr_forward: image too large"; return -1; }
+
+  char* gbuf = geometry_alloc(geometry_user, geom_bytes(P));
+  char* ibuf = image_alloc(image_user, image_bytes(width, height));
+  if (!gbuf || !ibuf) { g_err = "gsr_forward: scratch allocation failed"; return -1; }
+  GeomView g = carve_geom(aligned_base(gbuf), P);
+  ImageView im = carve_image(aligned_base(ibuf), width, height);
+
+  FwdArgs a;
+  a.P = P; a.D = D; a.M = M; a.W = width; a.H = height; a.gx = gx; a.gy = gy;
+  a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
+  a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+  a.view = viewmatrix; a.proj = projmatrix; a.campos = cam_pos;
+  a.scale_modifier = scale_modifier; a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+  a.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:225-226
+  a.focal_x = width / (2.0f * tan_fovx);
+  a.prefiltered = prefiltered; a.radii_out = radii;
+
+  const unsigned long long cap0 = r_capacity > 0 ? (unsigned long long)r_capacity : ~0ull;
+  if (!check(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * T, st), "memset tile_count")) return -1;
+  k_init_header<<<1, 1, 0, st>>>(im.hdr, cap0);
+  { Prof pf(0, st); launch_preprocess_fwd(a, g, im, st); }
+  if (!stage_ok(dbg, st, "preprocess_fwd")) return -1;
+  { Prof pf(1, st); launch_tile_scan(im, T, st); }
+  if (!stage_ok(dbg, st, "tile_scan")) return -1;
+
+  long long cap;
+  if (r_capacity > 0) {
+    cap = r_capacity;
+    if (r_host && !check(cudaMemcpyAsync(r_host, &im.hdr->num_rendered, 8, cudaMemcpyDeviceToHost, st), "async R")) return -1;
+  } else {
+    // exact mode: the one blocking read the reference also performs (rasterizer_impl.cu:284)
+    long long R = 0;
+    if (!check(cudaMemcpyAsync(&R, &im.hdr->num_rendered, 8, cudaMemcpyDeviceToHost, st), "read R")) return -1;
+    if (!check(cudaStreamSynchronize(st), "read R (sync)")) return -1;
+    if (r_host) *r_host = R;
+    cap = R;
+  }
+  char* bbuf = binning_alloc(binning_user, binning_bytes(cap));
+  if (!bbuf) { g_err = "gsr_forward: binning allocation failed"; return -1; }
+  BinView b = carve_binning(aligned_base(bbuf), cap);
+
+  if (cap > 0) {
+    { Prof pf(2, st); launch_scatter(P, gx, g, im, b, st); }
+    if (!stage_ok(dbg, st, "scatter")) return -1;
+    { Prof pf(3, st); launch_tile_sort(T, g, im, b, st); }
+    if (!stage_ok(dbg, st, "tile_sort")) return -1;
+  }
+  { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, out_color, out_depth, out_median_depth, out_opacity, st); }
+  if (!stage_ok(dbg, st, "render_fwd")) return -1;
+  return cap;
+}
+
+int gsr_backward(int P, int D, int M, int64_t R, const float* background, int width, int height,
+                 const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                 float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                 char* geom_buffer, char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                 const float* dL_dpix_depth, const float* dL_dpix_median_depth, const float* dL_dpix_final_opacity,
+                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug,
+                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool dbg = debug != 0;
+  if (P <= 0) return 0;
+  if (!geom_buffer || !image_buffer || (!binning_buffer && R > 0)) { g_err = "gsr_backward: missing state buffers"; return -1; }
+  if (!background) { g_err = "gsr_backward: background must be a device pointer (backward.cu:586 reads it)"; return -1; }
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  GeomView g = carve_geom(aligned_base(geom_buffer), P);
+  ImageView im = carve_image(aligned_base(image_buffer), width, height);
+  BinView b = carve_binning(aligned_base(binning_buffer), R);
+  if (radii == nullptr) radii = g.radii;  // rasterizer_impl.cu:381-384
+
+  if (!check(cudaMemsetAsync(g.grad, 0, sizeof(float) * GRAD_F * (size_t)P, st), "memset grad")) return -1;
+  if (R > 0) {
+    { Prof pf(5, st); launch_render_bwd(width, height, gx, gy, background, im, b, g, dL_dpix, dL_dpix_depth, dL_dpix_median_depth,
+                      dL_dpix_final_opacity, st); }
+    if (!stage_ok(dbg, st, "render_bwd")) return -1;
+  }
+  BwdArgs a;
+  a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+  a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales; a.rotations = rotations;
+  a.cov3D_precomp = cov3D_precomp; a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
+  a.scale_modifier = scale_modifier; a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+  a.focal_y = height / (2.0f * tan_fovy);
+  a.focal_x = width / (2.0f * tan_fovx);
+  a.radii = radii;
+  a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+  a.dL_ddepth = dL_ddepth; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
+  a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+  { Prof pf(6, st); launch_preprocess_bwd(a, g, st); }
+  if (!stage_ok(dbg, st, "preprocess_bwd")) return -1;
+  return 0;
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream) {
+  if (P <= 0) return 0;
+  launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "mark_visible") ? 0 : -1;
+}
+
+int gsr_depth2normal(const float* depth, int width, int height, float fx, float fy, float cx, float cy, float d_min,
+                     float d_max, const float* rot, float* out, void* stream) {
+  if (width <= 0 || height <= 0) return 0;
+  { Prof pf(7, (cudaStream_t)stream); launch_depth2normal(depth, width, height, fx, fy, cx, cy, d_min, d_max, rot, out, (cudaStream_t)stream); }
+  return check(cudaGetLastError(), "depth2normal") ? 0 : -1;
+}
+
+int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_buffer, const char* binning_buffer,
+                     const char* image_buffer, uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib,
+                     float* final_T, float* means2D, float* conic_opacity, float* depths, float* rgb, float* cov3D,
+                     uint32_t* tiles_touched, unsigned char* clamped, void* stream) {
+  GeomView g = carve_geom(aligned_base(const_cast<char*>(geom_buffer)), P);
+  ImageView im = carve_image(aligned_base(const_cast<char*>(image_buffer)), width, height);
+  BinView b = carve_binning(aligned_base(const_cast<char*>(binning_buffer)), R);
+  launch_debug_export(P, width, height, R, g, b, im, point_list, ranges, n_contrib, final_T, means2D, conic_opacity,
+                      depths, rgb, cov3D, tiles_touched, clamped, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "debug_export") ? 0 : -1;
+}
+
+int gsr_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int gsr_profile_read(float* ms, int* counts) {
+  std::lock_guard<std::mutex> l(g_prof_mu);
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      if (ms) ms[r.stage] += t;
+      if (counts) counts[r.stage] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
+
+}  // extern "C"

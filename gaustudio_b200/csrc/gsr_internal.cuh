@@ -1,0 +1,110 @@
+// Internal declarations of libgsr_b200: buffer layouts, launch wrappers, device helpers.
+// B200 (sm_100a) only.  Not part of the public ABI (that is include/gsr.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace gsr {
+
+constexpr int TILE_X = 16;  // observable behaviour of the reference (config.h:16-17)
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+
+// ---------------------------------------------------------------------------------------------
+// Per-Gaussian projected record ("splat"), 48 B = 3 x float4.  The same record is the element of the
+// per-tile slab that the render kernels stream with cp.async.bulk (TMA) into shared memory.
+//   q0 = { mean2D.x, mean2D.y, conic.A, conic.B }
+//   q1 = { conic.C, opacity, view-depth, rgb.r }
+//   q2 = { rgb.g, rgb.b, bits(gaussian index), bits(radius) }
+// ---------------------------------------------------------------------------------------------
+constexpr int SPLAT_F4 = 3;
+constexpr int SPLAT_BYTES = 48;
+constexpr int GRAD_F = 12;  // per-Gaussian screen-space gradient accumulator (10 used), 48 B
+
+struct ImageHeader {            // first 256 B of the image buffer
+  unsigned long long num_rendered;  // R = sum of tile counts (written by the scan kernel)
+  unsigned long long capacity;      // binning capacity the scatter / sort / render kernels may use
+  unsigned int overflow;            // set when num_rendered > capacity (pipelined mode)
+  unsigned int pad[11];
+};
+
+struct GeomView {      // carved from the geometry buffer, all 256-B aligned
+  float4* splat;       // [P][3]
+  uint2* rect;         // [P] packed tile rect: x = xmin | xmax<<16, y = ymin | ymax<<16
+  float* cov3D;        // [P][6]
+  unsigned char* clamped;  // [P] bit c set <=> channel c was clamped (forward.cu:66-68)
+  int* radii;          // [P] (internal copy; the caller's radii array is also written)
+  uint32_t* tiles_touched;  // [P]
+  float* grad;         // [P][GRAD_F] backward scratch
+};
+struct ImageView {
+  ImageHeader* hdr;
+  float* final_T;         // [H*W]
+  uint32_t* n_contrib;    // [H*W]
+  uint32_t* tile_count;   // [T]
+  uint2* tile_range;      // [T] [start,end) into the sorted instance list; (0,0) when empty
+  uint32_t* tile_cursor;  // [T]
+  uint32_t* tile_maxc;    // [T] max n_contrib over the tile's pixels (bounds the backward traversal)
+};
+struct BinView {
+  unsigned long long* ents;  // [cap] (depth bits << 32 | gaussian index), grouped by tile
+  float4* slab;              // [cap][3] sorted, gathered splat records
+};
+
+size_t geom_bytes(int P);
+size_t image_bytes(int W, int H);
+size_t binning_bytes(long long R);
+GeomView carve_geom(char* base, int P);
+ImageView carve_image(char* base, int W, int H);
+BinView carve_binning(char* base, long long cap);
+
+struct FwdArgs {
+  int P, D, M, W, H, gx, gy;
+  const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
+  const float *view, *proj, *campos;
+  float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
+  int prefiltered;
+  int* radii_out;
+};
+
+// ---- launch wrappers (each enqueues on `st`) ----
+void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st);
+void launch_tile_scan(ImageView im, int T, cudaStream_t st);
+void launch_scatter(int P, int gx, GeomView g, ImageView im, BinView b, cudaStream_t st);
+void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
+void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, float* out_color, float* out_depth,
+                       float* out_median, float* out_opacity, cudaStream_t st);
+void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
+                       const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
+                       const float* dL_dopacity, cudaStream_t st);
+
+struct BwdArgs {
+  int P, D, M, W, H;
+  const float *means3D, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+  const float *view, *proj, *campos;
+  float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
+  const int* radii;
+  float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_ddepth, *dL_dmean3D, *dL_dcov3D, *dL_dsh,
+      *dL_dscale, *dL_drot;
+};
+void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st);
+void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
+                         unsigned char* present, cudaStream_t st);
+void launch_depth2normal(const float* depth, int W, int H, float fx, float fy, float cx, float cy, float dmin,
+                         float dmax, const float* rot, float* out, cudaStream_t st);
+void launch_debug_export(int P, int W, int H, long long R, GeomView g, BinView b, ImageView im,
+                         uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib, float* final_T,
+                         float* means2D, float* conic_opacity, float* depths, float* rgb, float* cov3D,
+                         uint32_t* tiles_touched, unsigned char* clamped, cudaStream_t st);
+
+// ---- small device helpers shared by the kernels ----
+__device__ __forceinline__ uint2 pack_rect(int xmin, int ymin, int xmax, int ymax) {
+  return make_uint2((unsigned)xmin | ((unsigned)xmax << 16), (unsigned)ymin | ((unsigned)ymax << 16));
+}
+__device__ __forceinline__ void unpack_rect(uint2 r, int& xmin, int& ymin, int& xmax, int& ymax) {
+  xmin = r.x & 0xffff; xmax = r.x >> 16; ymin = r.y & 0xffff; ymax = r.y >> 16;
+}
+
+}  // namespace gsr

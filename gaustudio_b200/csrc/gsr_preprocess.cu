@@ -1,0 +1,492 @@
+// Per-Gaussian stages: projection (forward), fused cov2D/projection/SH/cov3D backward, frustum marking.
+//
+// Restates, with the reference's floating-point expression order (so that nvcc contracts the same FMAs
+// and radii / tile rects / depth keys come out bit-identical):
+//   forward : $RAST/cuda_rasterizer/forward.cu:20-71 (SH), 74-113 (cov2D), 118-152 (cov3D), 155-256 (K1)
+//   backward: $RAST/cuda_rasterizer/backward.cu:144-274 (K6), 346-412 (K7), 20-139 (SH), 278-341 (cov3D)
+//   helpers : $RAST/cuda_rasterizer/auxiliary.h:41-77,107-117,139-164
+// Design differences (B200): one packed 48-B splat record per Gaussian instead of five SoA arrays; per-tile
+// instance counts are accumulated here (no per-Gaussian prefix scan, no duplicateWithKeys offsets); K6 and
+// K7 are one kernel and write every output element (no torch::zeros pre-pass, rasterize_points.cu:160-169).
+#include "gsr_internal.cuh"
+
+#include <cstdio>
+
+namespace gsr {
+
+namespace {
+
+// SH basis constants (auxiliary.h:22-39)
+__device__ const float kC0 = 0.28209479177387814f;
+__device__ const float kC1 = 0.4886025119029199f;
+__device__ const float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+
+struct V3 { float x, y, z; };
+
+// column-major 3x3, m[c][r]; product written in the accumulation order of glm's mat3*mat3
+// (third_party/glm/glm/detail/type_mat3x3.inl:486-518) which the reference kernels inherit.
+struct Mat3 { float m[3][3]; };
+__device__ __forceinline__ Mat3 mmul(const Mat3& A, const Mat3& B) {
+  Mat3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+  return R;
+}
+__device__ __forceinline__ Mat3 mtr(const Mat3& A) {
+  Mat3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+  return R;
+}
+
+__device__ __forceinline__ V3 xf4x3(const V3& p, const float* __restrict__ m) {
+  V3 t;
+  t.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
+  t.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
+  t.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
+  return t;
+}
+__device__ __forceinline__ float4 xf4x4(const V3& p, const float* __restrict__ m) {
+  float4 t;
+  t.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
+  t.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
+  t.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
+  t.w = m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15];
+  return t;
+}
+
+// auxiliary.h:41-44: the 1.0 / 0.5 literals make this a double-precision expression
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// auxiliary.h:46-56
+__device__ __forceinline__ void tile_rect(float px, float py, int max_radius, int gx, int gy, int& x0, int& y0,
+                                          int& x1, int& y1) {
+  x0 = min(gx, max((int)0, (int)((px - max_radius) / TILE_X)));
+  y0 = min(gy, max((int)0, (int)((py - max_radius) / TILE_Y)));
+  x1 = min(gx, max((int)0, (int)((px + max_radius + TILE_X - 1) / TILE_X)));
+  y1 = min(gy, max((int)0, (int)((py + max_radius + TILE_Y - 1) / TILE_Y)));
+}
+
+struct Rot { Mat3 R; };
+// rotation from the un-normalised quaternion (r,x,y,z) exactly as forward.cu:127-139 (quirk 2)
+__device__ __forceinline__ Mat3 quat_mat(float r, float x, float y, float z) {
+  Mat3 R;
+  R.m[0][0] = 1.f - 2.f * (y * y + z * z);
+  R.m[0][1] = 2.f * (x * y - r * z);
+  R.m[0][2] = 2.f * (x * z + r * y);
+  R.m[1][0] = 2.f * (x * y + r * z);
+  R.m[1][1] = 1.f - 2.f * (x * x + z * z);
+  R.m[1][2] = 2.f * (y * z - r * x);
+  R.m[2][0] = 2.f * (x * z - r * y);
+  R.m[2][1] = 2.f * (y * z + r * x);
+  R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+  return R;
+}
+__device__ __forceinline__ Mat3 scale_mat(float sx, float sy, float sz) {
+  Mat3 S;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) S.m[c][r] = 0.0f;
+  S.m[0][0] = sx; S.m[1][1] = sy; S.m[2][2] = sz;
+  return S;
+}
+
+// forward.cu:74-113 / backward.cu:160-197: everything the two call sites share
+struct Cov2D {
+  V3 t;
+  float txtz, tytz, limx, limy;
+  Mat3 T, Vrk, Wm, cov;
+};
+__device__ __forceinline__ void cov2d(const V3& mean, float fx, float fy, float tan_fovx, float tan_fovy,
+                                      const float* cov3D, const float* __restrict__ view, Cov2D& o) {
+  o.t = xf4x3(mean, view);
+  o.limx = 1.3f * tan_fovx;
+  o.limy = 1.3f * tan_fovy;
+  o.txtz = o.t.x / o.t.z;
+  o.tytz = o.t.y / o.t.z;
+  o.t.x = min(o.limx, max(-o.limx, o.txtz)) * o.t.z;
+  o.t.y = min(o.limy, max(-o.limy, o.tytz)) * o.t.z;
+  Mat3 J;
+  J.m[0][0] = fx / o.t.z; J.m[0][1] = 0.0f; J.m[0][2] = -(fx * o.t.x) / (o.t.z * o.t.z);
+  J.m[1][0] = 0.0f; J.m[1][1] = fy / o.t.z; J.m[1][2] = -(fy * o.t.y) / (o.t.z * o.t.z);
+  J.m[2][0] = 0; J.m[2][1] = 0; J.m[2][2] = 0;
+  o.Wm.m[0][0] = view[0]; o.Wm.m[0][1] = view[4]; o.Wm.m[0][2] = view[8];
+  o.Wm.m[1][0] = view[1]; o.Wm.m[1][1] = view[5]; o.Wm.m[1][2] = view[9];
+  o.Wm.m[2][0] = view[2]; o.Wm.m[2][1] = view[6]; o.Wm.m[2][2] = view[10];
+  o.T = mmul(o.Wm, J);
+  o.Vrk.m[0][0] = cov3D[0]; o.Vrk.m[0][1] = cov3D[1]; o.Vrk.m[0][2] = cov3D[2];
+  o.Vrk.m[1][0] = cov3D[1]; o.Vrk.m[1][1] = cov3D[3]; o.Vrk.m[1][2] = cov3D[4];
+  o.Vrk.m[2][0] = cov3D[2]; o.Vrk.m[2][1] = cov3D[4]; o.Vrk.m[2][2] = cov3D[5];
+  o.cov = mmul(mmul(mtr(o.T), mtr(o.Vrk)), o.T);
+  o.cov.m[0][0] += 0.3f;
+  o.cov.m[1][1] += 0.3f;
+}
+
+// Count / scatter helper: visits every tile of every lane's rect.  Lanes with small rects loop themselves;
+// large rects (a splat covering much of the screen) are walked by the whole warp so one thread never
+// serialises thousands of atomics (the reference's duplicateWithKeys does, rasterizer_impl.cu:98-108).
+template <typename F>
+__device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, int gx, F f) {
+  const int w = x1 - x0, n = w * (y1 - y0);
+  const unsigned lane = threadIdx.x & 31;
+  constexpr int kBig = 32;
+  if (n > 0 && n <= kBig) {
+    for (int y = y0; y < y1; y++)
+      for (int x = x0; x < x1; x++) f(y * gx + x, lane);
+  }
+  unsigned big = __ballot_sync(0xffffffffu, n > kBig);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
+    for (int i = lane; i < bn; i += 32) f((by0 + i / bw) * gx + bx0 + i % bw, (unsigned)src);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: forward.cu:155-256
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  if (idx < a.P) {
+    int radius_i = 0;
+    uint32_t tiles = 0;
+    const V3 p = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+    // in_frustum (auxiliary.h:139-164): only the near plane is tested
+    const V3 p_view = xf4x3(p, a.view);
+    if (p_view.z <= 0.2f) {
+      if (a.prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+      }
+    } else {
+      const float4 p_hom = xf4x4(p, a.proj);
+      const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+      const float ppx = p_hom.x * p_w, ppy = p_hom.y * p_w;
+      float c3[6];
+      if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[6 * idx + k];
+      } else {
+        // computeCov3D, forward.cu:118-152
+        const float mod = a.scale_modifier;
+        const Mat3 S = scale_mat(mod * a.scales[3 * idx], mod * a.scales[3 * idx + 1], mod * a.scales[3 * idx + 2]);
+        const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        const Mat3 R = quat_mat(q.x, q.y, q.z, q.w);
+        const Mat3 Mm = mmul(S, R);
+        const Mat3 Sg = mmul(mtr(Mm), Mm);
+        c3[0] = Sg.m[0][0]; c3[1] = Sg.m[0][1]; c3[2] = Sg.m[0][2];
+        c3[3] = Sg.m[1][1]; c3[4] = Sg.m[1][2]; c3[5] = Sg.m[2][2];
+#pragma unroll
+        for (int k = 0; k < 6; k++) g.cov3D[6 * idx + k] = c3[k];
+      }
+      Cov2D cc;
+      cov2d(p, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, c3, a.view, cc);
+      const float cx = cc.cov.m[0][0], cy = cc.cov.m[0][1], cz = cc.cov.m[1][1];
+      const float det = (cx * cz - cy * cy);
+      if (det != 0.0f) {
+        const float det_inv = 1.f / det;
+        const float conA = cz * det_inv, conB = -cy * det_inv, conC = cx * det_inv;
+        const float mid = 0.5f * (cx + cz);
+        const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+        const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+        const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+        const float px = ndc2pix(ppx, a.W), py = ndc2pix(ppy, a.H);
+        tile_rect(px, py, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
+        if ((x1 - x0) * (y1 - y0) != 0) {
+          float rgb[3];
+          unsigned char cl = 0;
+          if (a.colors_precomp == nullptr) {
+            // computeColorFromSH, forward.cu:20-71 (coefficient stride M, degree D: quirk 13).  Written with
+            // explicit mul / fma intrinsics in the contraction the reference's sm_100a SASS ends up with (ptxas
+            // fuses its mul+add/sub pairs): weight_k rounded on its own, then res = fma(weight_k, sh_k, res).
+            const float* sh = a.shs + (size_t)idx * a.M * 3;
+            const float ox = p.x - a.campos[0], oy = p.y - a.campos[1], oz = p.z - a.campos[2];
+            const float len = sqrtf(__fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));  // glm::length
+            const float x = __fdiv_rn(ox, len), y = __fdiv_rn(oy, len), z = __fdiv_rn(oz, len);
+            float w[16];
+            int nco = 1;
+            if (a.D > 0) {
+              w[1] = -__fmul_rn(y, kC1); w[2] = __fmul_rn(z, kC1); w[3] = -__fmul_rn(x, kC1);
+              nco = 4;
+              if (a.D > 1) {
+                const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+                const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+                const float zz2 = __fadd_rn(zz, zz), d = __fsub_rn(xx, yy);
+                w[4] = __fmul_rn(xy, kC2[0]);
+                w[5] = __fmul_rn(yz, kC2[1]);
+                w[6] = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), kC2[2]);
+                w[7] = __fmul_rn(xz, kC2[3]);
+                w[8] = __fmul_rn(d, kC2[4]);
+                nco = 9;
+                if (a.D > 2) {
+                  const float v = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);  // 4zz - xx - yy
+                  w[9] = __fmul_rn(__fmul_rn(y, kC3[0]), __fmaf_rn(xx, 3.0f, -yy));
+                  w[10] = __fmul_rn(__fmul_rn(xy, kC3[1]), z);
+                  w[11] = __fmul_rn(__fmul_rn(y, kC3[2]), v);
+                  w[12] = __fmul_rn(__fmul_rn(z, kC3[3]), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+                  w[13] = __fmul_rn(__fmul_rn(x, kC3[4]), v);
+                  w[14] = __fmul_rn(__fmul_rn(z, kC3[5]), d);
+                  w[15] = __fmul_rn(__fmul_rn(x, kC3[6]), __fmaf_rn(yy, -3.0f, xx));
+                  nco = 16;
+                }
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              float res = __fmul_rn(sh[c], kC0);
+#pragma unroll
+              for (int k = 1; k < 16; k++)
+                if (k < nco) res = __fmaf_rn(w[k], sh[3 * k + c], res);
+              res = __fadd_rn(res, 0.5f);
+              if (res < 0) cl |= (1u << c);
+              rgb[c] = fmaxf(res, 0.0f);
+            }
+          } else {
+            rgb[0] = a.colors_precomp[3 * idx]; rgb[1] = a.colors_precomp[3 * idx + 1]; rgb[2] = a.colors_precomp[3 * idx + 2];
+          }
+          radius_i = (int)my_radius;
+          tiles = (uint32_t)((y1 - y0) * (x1 - x0));
+          g.clamped[idx] = cl;
+          float4* s = g.splat + (size_t)idx * SPLAT_F4;
+          s[0] = make_float4(px, py, conA, conB);
+          s[1] = make_float4(conC, a.opacities[idx], p_view.z, rgb[0]);
+          s[2] = make_float4(rgb[1], rgb[2], __int_as_float(idx), __int_as_float(radius_i));
+        }
+      }
+    }
+    if (tiles == 0) { x0 = y0 = x1 = y1 = 0; }
+    g.radii[idx] = radius_i;
+    if (a.radii_out) a.radii_out[idx] = radius_i;
+    g.tiles_touched[idx] = tiles;
+    g.rect[idx] = pack_rect(x0, y0, x1, y1);
+  }
+  // per-tile instance histogram (level 1 of the two-level binning; replaces InclusiveSum +
+  // duplicateWithKeys offsets, rasterizer_impl.cu:280-300)
+  for_each_tile(x0, y0, x1, y1, a.gx, [&](int tile, unsigned) { atomicAdd(&im.tile_count[tile], 1u); });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 + K7 fused: backward.cu:144-274 then 346-412 (K6 assigns dL_dmean, K7 accumulates: quirk 7)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+  const int M = a.M;
+  const bool vis = a.radii[idx] > 0;  // quirk 8
+  const float4* ga = reinterpret_cast<const float4*>(g.grad + (size_t)idx * GRAD_F);
+  float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
+  if (vis) { g0 = ga[0]; g1 = ga[1]; g2 = ga[2]; }
+  // accumulator layout (written by the render backward): g0 = {dcol.r, dcol.g, dcol.b, ddepth},
+  // g1 = {dopacity, dmean2D.x, dmean2D.y, dconic.xx}, g2 = {dconic.xy, dconic.yy, -, -}
+  const float dL_dcolor[3] = {g0.x, g0.y, g0.z};
+  const float dL_ddepth = g0.w, dL_dopac = g1.x, dm2x = g1.y, dm2y = g1.z;
+  const float dcon_x = g1.w, dcon_y = g2.x, dcon_w = g2.y;
+
+  a.dL_dmean2D[3 * idx] = dm2x; a.dL_dmean2D[3 * idx + 1] = dm2y; a.dL_dmean2D[3 * idx + 2] = 0.f;
+  a.dL_dopacity[idx] = dL_dopac;
+  a.dL_dcolor[3 * idx] = dL_dcolor[0]; a.dL_dcolor[3 * idx + 1] = dL_dcolor[1]; a.dL_dcolor[3 * idx + 2] = dL_dcolor[2];
+  if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
+  if (a.dL_ddepth) a.dL_ddepth[idx] = dL_ddepth;
+
+  float dmean[3] = {0.f, 0.f, 0.f};
+  float dcv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dsc[3] = {0.f, 0.f, 0.f};
+  float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* dsh = a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
+
+  if (vis) {
+    const V3 mean = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+    const float* cov3D = a.cov3D_precomp ? a.cov3D_precomp + 6 * idx : g.cov3D + 6 * idx;
+    float c3[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) c3[k] = cov3D[k];
+    Cov2D cc;
+    cov2d(mean, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, c3, a.view, cc);
+    const float x_grad_mul = cc.txtz < -cc.limx || cc.txtz > cc.limx ? 0 : 1;
+    const float y_grad_mul = cc.tytz < -cc.limy || cc.tytz > cc.limy ? 0 : 1;
+    const float ca = cc.cov.m[0][0], cb = cc.cov.m[0][1], cd = cc.cov.m[1][1];
+    const float denom = ca * cd - cb * cb;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const Mat3& T = cc.T;
+    if (denom2inv != 0) {
+      dL_da = denom2inv * (-cd * cd * dcon_x + 2 * cb * cd * dcon_y + (denom - ca * cd) * dcon_w);
+      dL_dc = denom2inv * (-ca * ca * dcon_w + 2 * ca * cb * dcon_y + (denom - ca * cd) * dcon_x);
+      dL_db = denom2inv * 2 * (cb * cd * dcon_x - (denom + 2 * cb * cb) * dcon_y + ca * cb * dcon_w);
+      dcv[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+      dcv[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+      dcv[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+      dcv[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
+      dcv[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
+      dcv[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+    }
+    const Mat3& V = cc.Vrk;
+    float dT0[3], dT1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float r0 = T.m[0][0] * V.m[j][0] + T.m[0][1] * V.m[j][1] + T.m[0][2] * V.m[j][2];
+      const float r1 = T.m[1][0] * V.m[j][0] + T.m[1][1] * V.m[j][1] + T.m[1][2] * V.m[j][2];
+      dT0[j] = 2 * r0 * dL_da + r1 * dL_db;
+      dT1[j] = 2 * r1 * dL_dc + r0 * dL_db;
+    }
+    const Mat3& Wm = cc.Wm;
+    const float dL_dJ00 = Wm.m[0][0] * dT0[0] + Wm.m[0][1] * dT0[1] + Wm.m[0][2] * dT0[2];
+    const float dL_dJ02 = Wm.m[2][0] * dT0[0] + Wm.m[2][1] * dT0[1] + Wm.m[2][2] * dT0[2];
+    const float dL_dJ11 = Wm.m[1][0] * dT1[0] + Wm.m[1][1] * dT1[1] + Wm.m[1][2] * dT1[2];
+    const float dL_dJ12 = Wm.m[2][0] * dT1[0] + Wm.m[2][1] * dT1[1] + Wm.m[2][2] * dT1[2];
+    const float tz = 1.f / cc.t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float hx = a.focal_x, hy = a.focal_y;
+    const float dL_dtx = x_grad_mul * -hx * tz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -hy * tz2 * dL_dJ12;
+    const float dL_dtz = -hx * tz2 * dL_dJ00 - hy * tz2 * dL_dJ11 + (2 * hx * cc.t.x) * tz3 * dL_dJ02 + (2 * hy * cc.t.y) * tz3 * dL_dJ12;
+    const float* vm = a.view;
+    dmean[0] = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;  // transformVec4x3Transpose
+    dmean[1] = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
+    dmean[2] = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
+
+    // ---- K7 (backward.cu:346-412)
+    const float* proj = a.proj;
+    const float4 m_hom = xf4x4(mean, proj);
+    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+    const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+    const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+    dmean[0] += (proj[0] * m_w - proj[3] * mul1) * dm2x + (proj[1] * m_w - proj[3] * mul2) * dm2y;
+    dmean[1] += (proj[4] * m_w - proj[7] * mul1) * dm2x + (proj[5] * m_w - proj[7] * mul2) * dm2y;
+    dmean[2] += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
+    const float mul3 = vm[2] * mean.x + vm[6] * mean.y + vm[10] * mean.z + vm[14];
+    dmean[0] += (vm[2] - vm[3] * mul3) * dL_ddepth;
+    dmean[1] += (vm[6] - vm[7] * mul3) * dL_ddepth;
+    dmean[2] += (vm[10] - vm[11] * mul3) * dL_ddepth;
+
+    if (a.shs) {
+      // SH backward, backward.cu:20-139
+      const float* sh = a.shs + (size_t)idx * M * 3;
+      const float ox = mean.x - a.campos[0], oy = mean.y - a.campos[1], oz = mean.z - a.campos[2];
+      const float len = sqrt(ox * ox + oy * oy + oz * oz);
+      const float x = ox / len, y = oy / len, z = oz / len;
+      const unsigned char cl = g.clamped[idx];
+      float dRGB[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) dRGB[c] = dL_dcolor[c] * ((cl >> c) & 1 ? 0.f : 1.f);
+      float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+      auto emit = [&](int k, float w, float bx, float by, float bz) {
+        // dL_dsh[k] = w * dRGB ; d(dir) += d(basis_k)/d(dir) * dot(sh[k], dRGB)
+        const float s = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
+        dsh[3 * k] = w * dRGB[0]; dsh[3 * k + 1] = w * dRGB[1]; dsh[3 * k + 2] = w * dRGB[2];
+        ddx += bx * s; ddy += by * s; ddz += bz * s;
+      };
+      emit(0, kC0, 0.f, 0.f, 0.f);
+      int used = 1;
+      if (a.D > 0) {
+        emit(1, -kC1 * y, 0.f, -kC1, 0.f);
+        emit(2, kC1 * z, 0.f, 0.f, kC1);
+        emit(3, -kC1 * x, -kC1, 0.f, 0.f);
+        used = 4;
+        if (a.D > 1) {
+          const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+          emit(4, kC2[0] * xy, kC2[0] * y, kC2[0] * x, 0.f);
+          emit(5, kC2[1] * yz, 0.f, kC2[1] * z, kC2[1] * y);
+          emit(6, kC2[2] * (2.f * zz - xx - yy), kC2[2] * 2.f * -x, kC2[2] * 2.f * -y, kC2[2] * 2.f * 2.f * z);
+          emit(7, kC2[3] * xz, kC2[3] * z, 0.f, kC2[3] * x);
+          emit(8, kC2[4] * (xx - yy), kC2[4] * 2.f * x, kC2[4] * 2.f * -y, 0.f);
+          used = 9;
+          if (a.D > 2) {
+            emit(9, kC3[0] * y * (3.f * xx - yy), kC3[0] * 3.f * 2.f * xy, kC3[0] * 3.f * (xx - yy), 0.f);
+            emit(10, kC3[1] * xy * z, kC3[1] * yz, kC3[1] * xz, kC3[1] * xy);
+            emit(11, kC3[2] * y * (4.f * zz - xx - yy), kC3[2] * -2.f * xy, kC3[2] * (-3.f * yy + 4.f * zz - xx), kC3[2] * 4.f * 2.f * yz);
+            emit(12, kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy), kC3[3] * -3.f * 2.f * xz, kC3[3] * -3.f * 2.f * yz, kC3[3] * 3.f * (2.f * zz - xx - yy));
+            emit(13, kC3[4] * x * (4.f * zz - xx - yy), kC3[4] * (-3.f * xx + 4.f * zz - yy), kC3[4] * -2.f * xy, kC3[4] * 4.f * 2.f * xz);
+            emit(14, kC3[5] * z * (xx - yy), kC3[5] * 2.f * xz, kC3[5] * -2.f * yz, kC3[5] * (xx - yy));
+            emit(15, kC3[6] * x * (xx - 3.f * yy), kC3[6] * 3.f * (xx - yy), kC3[6] * -3.f * 2.f * xy, 0.f);
+            used = 16;
+          }
+        }
+      }
+      for (int k = used; k < M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+      // dnormvdv (auxiliary.h:107-117)
+      const float sum2 = ox * ox + oy * oy + oz * oz;
+      const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+      dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+      dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+      dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+    }
+
+    if (a.scales) {
+      // cov3D backward, backward.cu:278-341 (gradient w.r.t. the un-normalised quaternion)
+      const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      const Mat3 R = quat_mat(r, x, y, z);
+      const float sx = a.scale_modifier * a.scales[3 * idx], sy = a.scale_modifier * a.scales[3 * idx + 1],
+                  sz = a.scale_modifier * a.scales[3 * idx + 2];
+      const Mat3 Mm = mmul(scale_mat(sx, sy, sz), R);
+      Mat3 dSg;
+      dSg.m[0][0] = dcv[0]; dSg.m[0][1] = 0.5f * dcv[1]; dSg.m[0][2] = 0.5f * dcv[2];
+      dSg.m[1][0] = 0.5f * dcv[1]; dSg.m[1][1] = dcv[3]; dSg.m[1][2] = 0.5f * dcv[4];
+      dSg.m[2][0] = 0.5f * dcv[2]; dSg.m[2][1] = 0.5f * dcv[4]; dSg.m[2][2] = dcv[5];
+      Mat3 M2;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) M2.m[c][rr] = Mm.m[c][rr] * 2.0f;
+      const Mat3 dM = mmul(M2, dSg);
+      const Mat3 Rt = mtr(R);
+      Mat3 dMt = mtr(dM);
+      dsc[0] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+      dsc[1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+      dsc[2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { dMt.m[0][k] *= sx; dMt.m[1][k] *= sy; dMt.m[2][k] *= sz; }
+      dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+      dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+      dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+      dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+    }
+  } else if (dsh) {
+    for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+  }
+  if (vis && dsh && !a.shs) {
+    for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+  }
+  a.dL_dmean3D[3 * idx] = dmean[0]; a.dL_dmean3D[3 * idx + 1] = dmean[1]; a.dL_dmean3D[3 * idx + 2] = dmean[2];
+#pragma unroll
+  for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * idx + k] = dcv[k];
+  a.dL_dscale[3 * idx] = dsc[0]; a.dL_dscale[3 * idx + 1] = dsc[1]; a.dL_dscale[3 * idx + 2] = dsc[2];
+  reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+}
+
+// checkFrustum, rasterizer_impl.cu:54-66
+__global__ void k_mark_visible(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                               unsigned char* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const V3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+  present[idx] = xf4x3(p, view).z > 0.2f;
+}
+
+}  // namespace
+
+void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st) {
+  k_preprocess_fwd<<<(a.P + 255) / 256, 256, 0, st>>>(a, g, im);
+}
+void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st) {
+  k_preprocess_bwd<<<(a.P + 255) / 256, 256, 0, st>>>(a, g);
+}
+void launch_mark_visible(int P, const float* means3D, const float* view, const float*, unsigned char* present,
+                         cudaStream_t st) {
+  k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, view, present);
+}
+
+}  // namespace gsr
