@@ -337,6 +337,7 @@ def main():
         roof = {"kernel": dom, "bound": "hbm", "achieved": stages_out[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": stages_out[dom]["frac"], "traffic": traffic.get(dom), "peak_source": peak_src,
                 "note": "FP32/SFU-bound compositing: HBM fraction is low by construction (DESIGN.md §Roofline)"}
+        stages_out["_kernels_ms"] = {k: round(v, 4) for k, v in stage_ms.items()}
         stages_out["_workload"] = {"R": R, "R_need": R_need, "P_visible": P_vis,
                                    "depth2normal_ms": round(stage_ms["depth2normal"], 4)}
 

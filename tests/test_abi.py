@@ -1,0 +1,48 @@
+"""The C-ABI library loads and exports every symbol include/gsr.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+from gaustudio_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "gsr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", src))
+    names.discard("gsr_alloc_fn")
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = _declared()
+    assert {"gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_depth2normal", "gsr_last_error"} <= names
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/gsr.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) <= names
+
+
+def test_host_only_entry_points():
+    L = _lib.lib()
+    assert L.gsr_abi_version() == 1
+    g1, g2 = L.gsr_geometry_bytes(1000), L.gsr_geometry_bytes(2000)
+    assert 0 < g1 < g2 and g2 < 2 * g1 + 8192
+    assert L.gsr_geometry_bytes(1_000_000) < 140 * 1_000_000  # ~121 B per Gaussian of forward+backward state
+    i1 = L.gsr_image_bytes(1920, 1080)
+    assert 8 * 1920 * 1080 <= i1 < 9 * 1920 * 1080 + 1_000_000
+    assert L.gsr_binning_bytes(0) >= 0 and L.gsr_binning_bytes(10**6) >= 56 * 10**6
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_no_oracle_import_in_product_path():
+    """The product package must not reference oracle/ (a CPU fallback would void the parity claims)."""
+    pkg = os.path.join(ROOT, "gaustudio_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert "from oracle" not in txt and "import oracle" not in txt and "gsr_oracle" not in txt, f

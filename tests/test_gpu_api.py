@@ -1,0 +1,158 @@
+"""-m gpu: plugin surface end to end, small ops, error/edge behaviour of the binding."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_util as U
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _model_and_cam(P=3000, W=120, H=90):
+    from gaustudio_b200.synthetic import build_config
+    model, cams, c = build_config("cfg1", P=P, W=W, H=H)
+    dev = torch.device("cuda")
+    return model.to(dev), cams[0].to(dev), dev
+
+
+def test_render_dict_and_backward_through_plugin():
+    from gaustudio_b200 import renderers
+    model, cam, dev = _model_and_cam()
+    model.requires_grad_(True)
+    r = renderers.make({"name": "vanilla_renderer"})
+    out = r.render(cam, model)
+    assert set(out) == {"render", "rendered_depth", "rendered_median_depth", "rendered_median_weight",
+                        "rendered_median_id", "viewspace_points", "visibility_filter", "rendered_final_opacity", "radii"}
+    assert out["render"].shape == (3, 90, 120) and out["rendered_depth"].shape == (1, 90, 120)
+    assert out["rendered_median_id"].dtype == torch.int32 and out["radii"].dtype == torch.int32
+    assert out["visibility_filter"].dtype == torch.bool and out["visibility_filter"].any()
+    (out["render"].mean() + out["rendered_depth"].mean() + out["rendered_final_opacity"].mean()).backward()
+    for p in model.parameters_list():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    assert out["viewspace_points"].grad is not None and out["viewspace_points"].grad[:, 2].abs().max() == 0
+    assert model._f_rest.grad.abs().max() > 0
+    # no_grad path (what every reference script uses) gives the same image
+    with torch.no_grad():
+        out2 = r.render(cam, model)
+    assert torch.equal(out["render"], out2["render"])
+
+
+def test_python_side_options_match_cuda_side():
+    from gaustudio_b200 import renderers
+    model, cam, dev = _model_and_cam()
+    model.get_covariance = lambda mod=1: _cov(model, mod)
+    a = renderers.make({"name": "vanilla_renderer"}).render(cam, model)
+    b = renderers.make({"name": "vanilla_renderer", "convert_SHs_python": True, "compute_cov3D_python": True}).render(cam, model)
+    assert (a["radii"] != b["radii"]).float().mean() < 1e-3
+    assert float((a["render"] - b["render"]).abs().max()) < 2e-3
+    w = renderers.make({"name": "vanilla_renderer", "white_background": True}).render(cam, model)
+    assert torch.equal(w["render"], a["render"])  # the forward never blends the background (quirk 1)
+
+
+def _cov(model, mod):
+    s = model.get_attribute("scale") * mod
+    q = model.get_attribute("rot")
+    R = torch.tensor(scenes.quat_to_mat(q.detach().cpu().numpy()), dtype=torch.float32, device=s.device)
+    M = R * s[:, None, :]
+    Sg = M @ M.transpose(1, 2)
+    return torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1)
+
+
+def test_mark_visible_and_depth2normal_against_oracle():
+    from gaustudio_b200 import ops
+    from gaustudio_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from oracle import oracle as orc, ref_torch_ops
+    s = scenes.scene("C")
+    dev = torch.device("cuda")
+    rs = GaussianRasterizationSettings(s["H"], s["W"], s["tanfovx"], s["tanfovy"], torch.zeros(3, device=dev), 1.0,
+                                       torch.tensor(s["viewmatrix"], device=dev), torch.tensor(s["projmatrix"], device=dev),
+                                       0, torch.tensor(s["campos"], device=dev), False, False)
+    vis = GaussianRasterizer(rs).markVisible(torch.tensor(s["means3D"], device=dev))
+    assert vis.dtype == torch.bool and np.array_equal(vis.cpu().numpy(), orc.mark_visible(s["means3D"], s["viewmatrix"]))
+    assert 0 < int(vis.sum()) < len(vis)
+    G = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "camera_golden.npz"))
+    for i in range(4):
+        K = G[f"c{i}_K"]
+        d = torch.tensor(G[f"c{i}_depth"], device=dev)
+        n = ops.depth2normal(d, K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+        assert float((n.cpu() - torch.tensor(G[f"c{i}_normal_cam"])).abs().max()) < 1e-4
+        ext = G[f"c{i}_view"].T
+        rot = torch.tensor(np.linalg.inv(ext[:3, :3].astype(np.float64)).T.astype(np.float32))
+        nw = ops.depth2normal(d, K[0, 0], K[1, 1], K[0, 2], K[1, 2], rot=rot)
+        assert float((nw.cpu() - torch.tensor(G[f"c{i}_normal_world"])).abs().max()) < 1e-4
+        nt = ref_torch_ops.depth2normal(d, torch.tensor(K))
+        assert float((n - nt).abs().max()) < 1e-4
+
+
+def test_camera_depth2normal_on_rendered_depth():
+    from gaustudio_b200 import renderers
+    from oracle import ref_torch_ops
+    model, cam, dev = _model_and_cam(P=20000, W=160, H=120)
+    with torch.no_grad():
+        out = renderers.make("vanilla_renderer").render(cam, model)
+    n = cam.depth2normal(out["rendered_depth"][0])
+    ref = ref_torch_ops.depth2normal(out["rendered_depth"][0], cam.intrinsics)
+    valid = (ref != -1).all(-1)
+    assert n.shape == (120, 160, 3) and bool(((n == -1).all(-1) == ~valid).all())
+    # normals of tiny depth differences amplify rounding: 1e-4 away from degenerate pixels, 1e-3 everywhere
+    assert float((n - ref).abs().max()) < 1e-3 and float((n - ref).abs()[valid].median()) < 1e-6
+
+
+def test_debug_mode_empty_input_and_side_stream():
+    from gaustudio_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    s = scenes.scene("A")
+    dev = torch.device("cuda")
+    base = scenes.run_torch(s, U.new_rasterize, dev)
+
+    def dbg(rs, *a, **kw):
+        return GaussianRasterizer(rs._replace(debug=True))(*a, **kw)
+    d = scenes.run_torch(s, dbg, dev)
+    assert np.array_equal(base["color"], d["color"])
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        side = scenes.run_torch(s, U.new_rasterize, dev)
+    st.synchronize()
+    assert np.array_equal(base["color"], side["color"]) and np.array_equal(base["radii"], side["radii"])
+    U.assert_grads_close(side["g_means3D"], base["g_means3D"], what="side stream")
+    # P == 0 short-circuit (rasterize_points.cu:84,171)
+    rs = GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3, device=dev), 1.0, torch.eye(4, device=dev),
+                                       torch.eye(4, device=dev), 0, torch.zeros(3, device=dev), False, False)
+    z = torch.zeros(0, 3, device=dev, requires_grad=True)
+    color, radii, depth, median, opac = GaussianRasterizer(rs)(z, z, torch.zeros(0, 1, device=dev),
+                                                               colors_precomp=torch.zeros(0, 3, device=dev),
+                                                               cov3D_precomp=torch.zeros(0, 6, device=dev))
+    assert color.shape == (3, 16, 16) and float(color.abs().max()) == 0 and radii.numel() == 0
+    color.sum().backward()
+    assert z.grad is not None and z.grad.shape == (0, 3)
+
+
+def test_large_tile_fallback_sort():
+    """More instances in one tile than fit the shared-memory sort (SORT_CAP): the global path must give the
+    same order (checked against the CPU oracle's point_list)."""
+    from gaustudio_b200 import _C
+    from oracle.oracle import Oracle
+    rng = np.random.RandomState(4)
+    P, W, H = 9000, 32, 32
+    cam = scenes.camera(W, H, 30.0, (3.0, 0.2, 0.1))
+    xyz = (0.05 * rng.randn(P, 3)).astype(np.float32)
+    sc = np.full((P, 3), 0.02, np.float32); rot = np.tile(np.array([1, 0, 0, 0], np.float32), (P, 1))
+    op = np.full((P, 1), 0.01, np.float32); col = rng.rand(P, 3).astype(np.float32)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)
+    e = torch.Tensor([])
+    args = (torch.zeros(3, device=dev), t(xyz), t(col), t(op), t(sc), t(rot), 1.0, e, cam.world_view_transform.to(dev),
+            cam.full_proj_transform.to(dev), math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), H, W, e, 0,
+            cam.camera_center.to(dev), False, False)
+    R, color, depth, median, opac, radii, gb, bb, ib = _C.rasterize_gaussians(*args)
+    ex = _C.debug_export(P, W, H, R, gb, bb, ib)
+    n = (ex["ranges"][:, 1] - ex["ranges"][:, 0])
+    assert int(n.max()) > 4096
+    o = Oracle()
+    out = o.forward(xyz, op, cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(), cam.camera_center.numpy(),
+                    math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), W, H, 0, colors_precomp=col, scales=sc, rotations=rot)
+    assert out["num_rendered"] == R
+    assert np.array_equal(o.binning()["point_list"], ex["point_list"].cpu().numpy().astype(np.uint32))
+    U.assert_images_close(color.cpu().numpy(), out["color"], atol=1e-4, outlier_frac=2e-3, what="color")
