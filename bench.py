@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--config", default="cfg3")
     ap.add_argument("--gaussians", type=int, default=None, help="override P (debug only; invalidates the number)")
     ap.add_argument("--pipelined", type=int, default=1, help="sync-free forward (capacity from high-water mark)")
+    ap.add_argument("--fused", type=int, default=1, help="fused activations inside the projection kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -110,9 +111,10 @@ class HostCamera:
         return self
 
 
-def make_step(impl, model, dev, H, W):
+def make_step(impl, model, dev, H, W, fused=True):
     """Returns step(cam) -> scalar loss tensor (on device).  Same loop for both arms; only the rasterizer and the
     depth->normal op differ (reference: its CUDA extension + its torch depth2normal)."""
+    import torch.nn.functional as F
     from gaustudio_b200 import ops, renderers
     g = torch.Generator().manual_seed(1234)
     tc = torch.rand(3, H, W, generator=g).to(dev)
@@ -121,7 +123,7 @@ def make_step(impl, model, dev, H, W):
     params = model.parameters_list()
 
     if impl == "new":
-        renderer = renderers.make({"name": "vanilla_renderer"})
+        renderer = renderers.make({"name": "vanilla_renderer", "fused_activations": bool(fused)})
 
         def render(cam):
             return renderer.render(cam, model)
@@ -153,8 +155,8 @@ def make_step(impl, model, dev, H, W):
         for p in params:
             p.grad = None
         out = render(cam)
-        loss = (out["render"] - tc).abs().mean() + 0.1 * (out["rendered_depth"] - td).abs().mean() + \
-            0.1 * (out["rendered_final_opacity"] - to).abs().mean()
+        loss = F.l1_loss(out["render"], tc) + 0.1 * F.l1_loss(out["rendered_depth"], td) + \
+            0.1 * F.l1_loss(out["rendered_final_opacity"], to)
         loss.backward()
         n = normal(cam, out["rendered_depth"].detach()[0])
         return loss.detach() + 0.0 * n[0, 0, 0]
@@ -226,7 +228,7 @@ def main():
     model.to(dev).requires_grad_(True)
     D = model.active_sh_degree
     H, W, P = c["H"], c["W"], c["P"]
-    step = make_step(a.impl, model, dev, H, W)
+    step = make_step(a.impl, model, dev, H, W, fused=a.fused)
     if a.impl == "new":
         _C.set_pipelined(bool(a.pipelined))
 
@@ -353,6 +355,8 @@ def main():
                                "fwd+bwd (L1 colour + 0.1 L1 depth + 0.1 L1 opacity) + depth->normal",
                    "views_total": nviews_total, "parallelism": f"view-sharded x{world}",
                    "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 66 MB of per-view outputs vs 126 MB)",
+                   "activations": ("fused into the projection kernel (fused_activations=True)" if a.fused and
+                                   a.impl == "new" else "torch ops per view (reference op sequence)"),
                    "forward_mode": "pipelined (no host sync; overflow-checked)" if a.pipelined and a.impl == "new" else
                                    "exact (one blocking 8-byte D2H per view, like the reference)"},
         "clocks": clocks,

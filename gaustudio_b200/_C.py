@@ -23,6 +23,8 @@ def set_pipelined(enabled, slack=1.5):
     _pipeline.slack = float(slack)
     _pipeline.hw = {}
     _pipeline.pending = []
+    _pipeline.ring = None   # pinned int64 ring: one slot per in-flight view (no allocation in the hot path)
+    _pipeline.slot = 0
 
 
 def _pl():
@@ -57,6 +59,21 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_bg_cache = {}
+
+
+def _bg_on(t, device):
+    """gaustudio keeps the background colour on the CPU (vanilla_renderer.py:23).  A per-call `.to(device)` of a
+    pageable tensor is a blocking copy that drains the stream, so device copies are cached by value."""
+    if t.device == device:
+        return t
+    key = (tuple(float(v) for v in t.flatten().tolist()), device.index)
+    d = _bg_cache.get(key)
+    if d is None:
+        d = _bg_cache[key] = t.to(device=device, dtype=torch.float32).contiguous()
+    return d
+
+
 def _f32(t, device, name):
     if t is None or t.numel() == 0:
         return t
@@ -82,7 +99,9 @@ class _Arena:
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug):
+                        prefiltered, debug, _fused=None):
+    """_fused=(f_dc, f_rest): fused-activation variant (gsr_forward_fused): `opacity`, `scales`, `rotations` are
+    then the model's RAW attributes and `sh` / `colors` / `cov3D_precomp` are ignored."""
     if means3D.ndimension() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
     if not means3D.is_cuda:
@@ -100,8 +119,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     rotations = _f32(rotations, dev, "rotations"); cov3D_precomp = _f32(cov3D_precomp, dev, "cov3D_precomp")
     viewmatrix = _f32(viewmatrix, dev, "viewmatrix"); projmatrix = _f32(projmatrix, dev, "projmatrix")
     sh = _f32(sh, dev, "shs"); campos = _f32(campos, dev, "campos")
-    background = _f32(background, dev, "bg")  # gaustudio passes a CPU tensor (vanilla_renderer.py:23)
+    background = _f32(_bg_on(background, dev), dev, "bg")  # gaustudio passes a CPU tensor
     M = sh.size(1) if sh.numel() != 0 else 0  # rasterize_points.cu:86-90
+    if _fused is not None:
+        f_dc, f_rest = (_f32(t, dev, "f_dc/f_rest") for t in _fused)
+        M = 1 + (f_rest.numel() // (3 * P) if f_rest.numel() else 0)
 
     out_color = torch.empty(3, H, W, **fopt); out_depth = torch.empty(1, H, W, **fopt)
     out_median = torch.empty(3, H, W, **fopt); out_opacity = torch.empty(1, H, W, **fopt)
@@ -114,15 +136,28 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     if pl.enabled:
         check_pipeline()
         cap = pl.hw.get(key, 0)
-        host = torch.empty(1, dtype=torch.int64).pin_memory()
+        if cap > 0:
+            if pl.ring is None:
+                pl.ring = torch.zeros(256, dtype=torch.int64).pin_memory()
+            if len(pl.pending) >= 200:
+                check_pipeline(wait=True)
+            host = pl.ring[pl.slot:pl.slot + 1]
+            pl.slot = (pl.slot + 1) % 256
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
-        r = L.gsr_forward(geom.fn, None, binning.fn, None, img.fn, None, P, int(degree), M, _ptr(background), W, H,
-                          _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales), float(scale_modifier),
-                          _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
-                          float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), _ptr(out_color), _ptr(out_depth),
-                          _ptr(out_median), _ptr(out_opacity), _ptr(radii), int(bool(debug)), int(cap),
-                          C.c_void_p(host.data_ptr()) if host is not None else None, C.c_void_p(stream.cuda_stream))
+        tail = (float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), _ptr(out_color), _ptr(out_depth),
+                _ptr(out_median), _ptr(out_opacity), _ptr(radii), int(bool(debug)), int(cap),
+                C.c_void_p(host.data_ptr()) if host is not None else None, C.c_void_p(stream.cuda_stream))
+        if _fused is None:
+            r = L.gsr_forward(geom.fn, None, binning.fn, None, img.fn, None, P, int(degree), M, _ptr(background), W, H,
+                              _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
+                              float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
+                              _ptr(projmatrix), _ptr(campos), *tail)
+        else:
+            r = L.gsr_forward_fused(geom.fn, None, binning.fn, None, img.fn, None, P, int(degree), M, _ptr(background),
+                                    W, H, _ptr(means3D), _ptr(f_dc), _ptr(f_rest), _ptr(opacity), _ptr(scales),
+                                    float(scale_modifier), _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix),
+                                    _ptr(campos), *tail)
         if r < 0:
             raise RuntimeError("gsr_forward failed: " + _lib.last_error())
         if pl.enabled:
@@ -154,7 +189,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         scales = _f32(scales, dev, "scales"); rotations = _f32(rotations, dev, "rotations")
         cov3D_precomp = _f32(cov3D_precomp, dev, "cov3D_precomp"); viewmatrix = _f32(viewmatrix, dev, "viewmatrix")
         projmatrix = _f32(projmatrix, dev, "projmatrix"); sh = _f32(sh, dev, "shs"); campos = _f32(campos, dev, "campos")
-        background = _f32(background, dev, "bg")
+        background = _f32(_bg_on(background, dev), dev, "bg")
         gc = _f32(dL_dout_color, dev, "dL_dout_color"); gd = _f32(dL_dout_depth, dev, "dL_dout_depth")
         gm = _f32(dL_dout_median_depth, dev, "dL_dout_median_depth")
         go = _f32(dL_dout_final_opacity, dev, "dL_dout_final_opacity")
@@ -172,6 +207,42 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         if rc < 0:
             raise RuntimeError("gsr_backward failed: " + _lib.last_error())
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def rasterize_gaussians_fused_backward(background, means3D, radii, f_dc, f_rest, opacity_logits, log_scales,
+                                       raw_rotations, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                       dL_dout_color, dL_dout_depth, dL_dout_median_depth, dL_dout_final_opacity,
+                                       degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+    """Backward of the fused-activation variant: gradients w.r.t. the RAW attributes
+    -> (dL_dmeans2D, dL_dopacity_logit, dL_dmeans3D, dL_df_dc, dL_df_rest, dL_dlog_scale, dL_draw_rot)."""
+    L = _lib.lib()
+    dev = means3D.device
+    P = means3D.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    fopt = dict(dtype=torch.float32, device=dev)
+    f_dc, f_rest = _f32(f_dc, dev, "f_dc"), _f32(f_rest, dev, "f_rest")
+    M = 1 + (f_rest.numel() // (3 * P) if f_rest.numel() else 0)
+    d_m3 = torch.empty(P, 3, **fopt); d_m2 = torch.empty(P, 3, **fopt); d_op = torch.empty_like(opacity_logits)
+    d_dc = torch.empty_like(f_dc); d_rest = torch.empty_like(f_rest); d_sc = torch.empty(P, 3, **fopt)
+    d_rot = torch.empty(P, 4, **fopt); d_col = torch.empty(P, 3, **fopt); d_cov = torch.empty(P, 6, **fopt)
+    means3D = _f32(means3D, dev, "means3D"); opacity_logits = _f32(opacity_logits, dev, "opacity")
+    log_scales = _f32(log_scales, dev, "scales"); raw_rotations = _f32(raw_rotations, dev, "rotations")
+    viewmatrix = _f32(viewmatrix, dev, "viewmatrix"); projmatrix = _f32(projmatrix, dev, "projmatrix")
+    campos = _f32(campos, dev, "campos"); background = _f32(_bg_on(background, dev), dev, "bg")
+    gc = _f32(dL_dout_color, dev, "dL_dout_color"); gd = _f32(dL_dout_depth, dev, "dL_dout_depth")
+    gm = _f32(dL_dout_median_depth, dev, "dL_dout_median_depth"); go = _f32(dL_dout_final_opacity, dev, "dL_dout_opacity")
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        rc = L.gsr_backward_fused(P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(f_dc),
+                                  _ptr(f_rest), _ptr(opacity_logits), _ptr(log_scales), float(scale_modifier),
+                                  _ptr(raw_rotations), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx),
+                                  float(tan_fovy), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                                  _ptr(gc), _ptr(gd), _ptr(gm), _ptr(go), _ptr(d_m2), _ptr(d_op), _ptr(d_col), _ptr(d_m3),
+                                  _ptr(d_cov), _ptr(d_dc), _ptr(d_rest), _ptr(d_sc), _ptr(d_rot), int(bool(debug)),
+                                  C.c_void_p(stream.cuda_stream))
+    if rc < 0:
+        raise RuntimeError("gsr_backward_fused failed: " + _lib.last_error())
+    return d_m2, d_op, d_m3, d_dc, d_rest, d_sc, d_rot
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -22,6 +22,10 @@ SIGNATURES = {
                          _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _I, _L, _P, _P]),
     "gsr_backward": (_I, [_I, _I, _I, _L, _P, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P,
                           _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "gsr_forward_fused": (_L, [ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _F, _P,
+                               _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _I, _L, _P, _P]),
+    "gsr_backward_fused": (_I, [_I, _I, _I, _L, _P, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _F, _F, _P, _P, _P,
+                                _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "gsr_mark_visible": (_I, [_I, _P, _P, _P, _P, _P]),
     "gsr_depth2normal": (_I, [_P, _I, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     "gsr_profile_enable": (_I, [_I]),

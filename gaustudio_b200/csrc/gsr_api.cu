@@ -80,9 +80,9 @@ ImageView carve_image(char* base, int W, int H) {
   take(p, im.hdr, 1);
   take(p, im.final_T, N);
   take(p, im.n_contrib, N);
-  take(p, im.tile_count, T);
+  take(p, im.tile_count, T * SUBBINS);
   take(p, im.tile_range, T);
-  take(p, im.tile_cursor, T);
+  take(p, im.tile_cursor, T * SUBBINS);
   take(p, im.tile_maxc, T);
   return im;
 }
@@ -210,7 +210,7 @@ size_t gsr_geometry_bytes(int P) { return geom_bytes(P); }
 size_t gsr_image_bytes(int width, int height) { return image_bytes(width, height); }
 size_t gsr_binning_bytes(int64_t num_rendered) { return binning_bytes(num_rendered); }
 
-int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc, void* binning_user,
+static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc, void* binning_user,
                     gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background,
                     int width, int height, const float* means3D, const float* shs, const float* colors_precomp,
                     const float* opacities, const float* scales, float scale_modifier, const float* rotations,
@@ -222,9 +222,10 @@ int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_
   cudaStream_t st = (cudaStream_t)stream;
   const bool dbg = debug != 0;
   if (P <= 0 || width <= 0 || height <= 0) { g_err = "gsr_forward: P, width and height must be positive"; return -1; }
-  if (colors_precomp == nullptr && shs == nullptr) { g_err = "gsr_forward: need shs or colors_precomp"; return -1; }
+  if (colors_precomp == nullptr && shs == nullptr && !fused) { g_err = "gsr_forward: need shs or colors_precomp"; return -1; }
+  if (fused && (!f_dc || (M > 1 && !f_rest) || !scales || !rotations || M < 1)) { g_err = "gsr_forward_fused: need f_dc, f_rest, raw scales and rotations"; return -1; }
   if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr)) { g_err = "gsr_forward: need scales+rotations or cov3D_precomp"; return -1; }
-  if (D < 0 || D > 3 || (shs && (D + 1) * (D + 1) > M)) { g_err = "gsr_forward: sh degree / coefficient count mismatch"; return -1; }
+  if (D < 0 || D > 3 || ((shs || fused) && (D + 1) * (D + 1) > M)) { g_err = "gsr_forward: sh degree / coefficient count mismatch"; return -1; }
   const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y, T = gx * gy;
   if (gx > 65535 || gy > 65535) { g_err = "gsr_forward: image too large"; return -1; }
 
@@ -243,9 +244,10 @@ int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_
   a.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:225-226
   a.focal_x = width / (2.0f * tan_fovx);
   a.prefiltered = prefiltered; a.radii_out = radii;
+  a.fused = fused; a.f_dc = f_dc; a.f_rest = f_rest;
 
   const unsigned long long cap0 = r_capacity > 0 ? (unsigned long long)r_capacity : ~0ull;
-  if (!check(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * T, st), "memset tile_count")) return -1;
+  if (!check(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * T * SUBBINS, st), "memset tile_count")) return -1;
   k_init_header<<<1, 1, 0, st>>>(im.hdr, cap0);
   { Prof pf(0, st); launch_preprocess_fwd(a, g, im, st); }
   if (!stage_ok(dbg, st, "preprocess_fwd")) return -1;
@@ -269,7 +271,7 @@ int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_
   BinView b = carve_binning(aligned_base(bbuf), cap);
 
   if (cap > 0) {
-    { Prof pf(2, st); launch_scatter(P, gx, g, im, b, st); }
+    { Prof pf(2, st); launch_scatter(P, gx, T, g, im, b, st); }
     if (!stage_ok(dbg, st, "scatter")) return -1;
     { Prof pf(3, st); launch_tile_sort(T, g, im, b, st); }
     if (!stage_ok(dbg, st, "tile_sort")) return -1;
@@ -279,7 +281,7 @@ int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_
   return cap;
 }
 
-int gsr_backward(int P, int D, int M, int64_t R, const float* background, int width, int height,
+static int backward_impl(int fused, const float* f_dc, const float* f_rest, const float* opacities_raw, float* dL_df_dc, float* dL_df_rest, int P, int D, int M, int64_t R, const float* background, int width, int height,
                  const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                  float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
                  const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
@@ -316,9 +318,73 @@ int gsr_backward(int P, int D, int M, int64_t R, const float* background, int wi
   a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
   a.dL_ddepth = dL_ddepth; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+  a.fused = fused; a.f_dc = f_dc; a.f_rest = f_rest; a.opacities_raw = opacities_raw;
+  a.dL_df_dc = dL_df_dc; a.dL_df_rest = dL_df_rest;
   { Prof pf(6, st); launch_preprocess_bwd(a, g, st); }
   if (!stage_ok(dbg, st, "preprocess_bwd")) return -1;
   return 0;
+}
+
+int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc, void* binning_user,
+                    gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background,
+                    int width, int height, const float* means3D, const float* shs, const float* colors_precomp,
+                    const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+                    const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                    const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                    float* out_depth, float* out_median_depth, float* out_opacity, int* radii, int debug,
+                    int64_t r_capacity, int64_t* r_host, void* stream) {
+  return forward_impl(0, nullptr, nullptr, geometry_alloc, geometry_user, binning_alloc, binning_user, image_alloc,
+                      image_user, P, D, M, background, width, height, means3D, shs, colors_precomp, opacities, scales,
+                      scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+                      prefiltered, out_color, out_depth, out_median_depth, out_opacity, radii, debug, r_capacity, r_host,
+                      stream);
+}
+
+int64_t gsr_forward_fused(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc,
+                          void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
+                          const float* background, int width, int height, const float* means3D, const float* f_dc,
+                          const float* f_rest, const float* opacity_logits, const float* log_scales,
+                          float scale_modifier, const float* raw_rotations, const float* viewmatrix,
+                          const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                          int prefiltered, float* out_color, float* out_depth, float* out_median_depth,
+                          float* out_opacity, int* radii, int debug, int64_t r_capacity, int64_t* r_host, void* stream) {
+  return forward_impl(1, f_dc, f_rest, geometry_alloc, geometry_user, binning_alloc, binning_user, image_alloc,
+                      image_user, P, D, M, background, width, height, means3D, nullptr, nullptr, opacity_logits,
+                      log_scales, scale_modifier, raw_rotations, nullptr, viewmatrix, projmatrix, cam_pos, tan_fovx,
+                      tan_fovy, prefiltered, out_color, out_depth, out_median_depth, out_opacity, radii, debug,
+                      r_capacity, r_host, stream);
+}
+
+int gsr_backward(int P, int D, int M, int64_t R, const float* background, int width, int height,
+                 const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                 float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                 char* geom_buffer, char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                 const float* dL_dpix_depth, const float* dL_dpix_median_depth, const float* dL_dpix_final_opacity,
+                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug,
+                 void* stream) {
+  return backward_impl(0, nullptr, nullptr, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D,
+                       shs, colors_precomp, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                       campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
+                       dL_dpix_depth, dL_dpix_median_depth, dL_dpix_final_opacity, dL_dmean2D, dL_dconic, dL_dopacity,
+                       dL_dcolor, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream);
+}
+
+int gsr_backward_fused(int P, int D, int M, int64_t R, const float* background, int width, int height,
+                       const float* means3D, const float* f_dc, const float* f_rest, const float* opacity_logits,
+                       const float* log_scales, float scale_modifier, const float* raw_rotations,
+                       const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                       float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                       const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dpix_median_depth,
+                       const float* dL_dpix_final_opacity, float* dL_dmean2D, float* dL_dopacity_logit,
+                       float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_df_dc, float* dL_df_rest,
+                       float* dL_dlog_scale, float* dL_draw_rot, int debug, void* stream) {
+  return backward_impl(1, f_dc, f_rest, opacity_logits, dL_df_dc, dL_df_rest, P, D, M, R, background, width, height,
+                       means3D, nullptr, nullptr, log_scales, scale_modifier, raw_rotations, nullptr, viewmatrix,
+                       projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
+                       dL_dpix_depth, dL_dpix_median_depth, dL_dpix_final_opacity, dL_dmean2D, nullptr, dL_dopacity_logit,
+                       dL_dcolor, nullptr, dL_dmean3D, dL_dcov3D, nullptr, dL_dlog_scale, dL_draw_rot, debug, stream);
 }
 
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

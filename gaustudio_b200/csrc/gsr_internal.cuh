@@ -11,6 +11,10 @@ namespace gsr {
 constexpr int TILE_X = 16;  // observable behaviour of the reference (config.h:16-17)
 constexpr int TILE_Y = 16;
 constexpr int TILE_PIX = TILE_X * TILE_Y;
+// Level-1 binning counters are split into SUBBINS independent counters per tile (chosen by the Gaussian
+// index) laid out sub-bin-major, so that the returning atomics of the scatter pass do not serialise on one
+// L2 address per hot tile.  A tile's instances are the concatenation of its sub-bin segments.
+constexpr int SUBBINS = 16;
 
 // ---------------------------------------------------------------------------------------------
 // Per-Gaussian projected record ("splat"), 48 B = 3 x float4.  The same record is the element of the
@@ -43,9 +47,9 @@ struct ImageView {
   ImageHeader* hdr;
   float* final_T;         // [H*W]
   uint32_t* n_contrib;    // [H*W]
-  uint32_t* tile_count;   // [T]
+  uint32_t* tile_count;   // [SUBBINS][T] instance histogram (sub-bin major)
   uint2* tile_range;      // [T] [start,end) into the sorted instance list; (0,0) when empty
-  uint32_t* tile_cursor;  // [T]
+  uint32_t* tile_cursor;  // [SUBBINS][T] write cursors of the scatter pass
   uint32_t* tile_maxc;    // [T] max n_contrib over the tile's pixels (bounds the backward traversal)
 };
 struct BinView {
@@ -67,12 +71,17 @@ struct FwdArgs {
   float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
   int prefiltered;
   int* radii_out;
+  // fused-activation variant (gsr_forward_fused): scales / rotations / opacities are the model's RAW
+  // attributes (log-scale, un-normalised quaternion, opacity logit) and the SH tensor arrives as its two
+  // stored pieces f_dc [P,1,3] + f_rest [P,M-1,3]; the kernel applies exp / normalize / sigmoid / cat itself.
+  int fused;
+  const float *f_dc, *f_rest;
 };
 
 // ---- launch wrappers (each enqueues on `st`) ----
 void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st);
 void launch_tile_scan(ImageView im, int T, cudaStream_t st);
-void launch_scatter(int P, int gx, GeomView g, ImageView im, BinView b, cudaStream_t st);
+void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
 void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, float* out_color, float* out_depth,
                        float* out_median, float* out_opacity, cudaStream_t st);
@@ -88,6 +97,10 @@ struct BwdArgs {
   const int* radii;
   float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_ddepth, *dL_dmean3D, *dL_dcov3D, *dL_dsh,
       *dL_dscale, *dL_drot;
+  // fused-activation variant (gsr_backward_fused): raw inputs, gradients w.r.t. the raw attributes
+  int fused;
+  const float *f_dc, *f_rest, *opacities_raw;
+  float *dL_df_dc, *dL_df_rest;
 };
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st);
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
@@ -100,6 +113,14 @@ void launch_debug_export(int P, int W, int H, long long R, GeomView g, BinView b
                          uint32_t* tiles_touched, unsigned char* clamped, cudaStream_t st);
 
 // ---- small device helpers shared by the kernels ----
+// model activations of gaustudio's VanillaPointCloud (models/vanilla_sg.py:29-35, models/utils.py:6-32)
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float4 act_normalize(float4 q, float* inv_norm = nullptr) {
+  const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);  // F.normalize eps
+  if (inv_norm) *inv_norm = 1.0f / n;
+  return make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+}
+__device__ __forceinline__ int subbin_of(int gaussian_idx) { return gaussian_idx & (SUBBINS - 1); }
 __device__ __forceinline__ uint2 pack_rect(int xmin, int ymin, int xmax, int ymax) {
   return make_uint2((unsigned)xmin | ((unsigned)xmax << 16), (unsigned)ymin | ((unsigned)ymax << 16));
 }

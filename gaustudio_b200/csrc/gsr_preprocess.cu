@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
       } else {
         // computeCov3D, forward.cu:118-152
         const float mod = a.scale_modifier;
-        const Mat3 S = scale_mat(mod * a.scales[3 * idx], mod * a.scales[3 * idx + 1], mod * a.scales[3 * idx + 2]);
-        const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        float s0 = a.scales[3 * idx], s1 = a.scales[3 * idx + 1], s2 = a.scales[3 * idx + 2];
+        float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        if (a.fused) { s0 = expf(s0); s1 = expf(s1); s2 = expf(s2); q = act_normalize(q); }
+        const Mat3 S = scale_mat(mod * s0, mod * s1, mod * s2);
         const Mat3 R = quat_mat(q.x, q.y, q.z, q.w);
         const Mat3 Mm = mmul(S, R);
         const Mat3 Sg = mmul(mtr(Mm), Mm);
@@ -212,7 +214,9 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
             // computeColorFromSH, forward.cu:20-71 (coefficient stride M, degree D: quirk 13).  Written with
             // explicit mul / fma intrinsics in the contraction the reference's sm_100a SASS ends up with (ptxas
             // fuses its mul+add/sub pairs): weight_k rounded on its own, then res = fma(weight_k, sh_k, res).
-            const float* sh = a.shs + (size_t)idx * a.M * 3;
+            // coefficient 0 and coefficients >= 1 may live in two tensors (fused path: f_dc / f_rest)
+            const float* sh0 = a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * a.M * 3;
+            const float* shr = a.fused ? a.f_rest + (size_t)idx * (a.M - 1) * 3 : sh0 + 3;
             const float ox = p.x - a.campos[0], oy = p.y - a.campos[1], oz = p.z - a.campos[2];
             const float len = sqrtf(__fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));  // glm::length
             const float x = __fdiv_rn(ox, len), y = __fdiv_rn(oy, len), z = __fdiv_rn(oz, len);
@@ -246,10 +250,10 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
             }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-              float res = __fmul_rn(sh[c], kC0);
+              float res = __fmul_rn(sh0[c], kC0);
 #pragma unroll
               for (int k = 1; k < 16; k++)
-                if (k < nco) res = __fmaf_rn(w[k], sh[3 * k + c], res);
+                if (k < nco) res = __fmaf_rn(w[k], shr[3 * (k - 1) + c], res);
               res = __fadd_rn(res, 0.5f);
               if (res < 0) cl |= (1u << c);
               rgb[c] = fmaxf(res, 0.0f);
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
           g.clamped[idx] = cl;
           float4* s = g.splat + (size_t)idx * SPLAT_F4;
           s[0] = make_float4(px, py, conA, conB);
-          s[1] = make_float4(conC, a.opacities[idx], p_view.z, rgb[0]);
+          s[1] = make_float4(conC, a.fused ? act_sigmoid(a.opacities[idx]) : a.opacities[idx], p_view.z, rgb[0]);
           s[2] = make_float4(rgb[1], rgb[2], __int_as_float(idx), __int_as_float(radius_i));
         }
       }
@@ -275,7 +279,10 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
   }
   // per-tile instance histogram (level 1 of the two-level binning; replaces InclusiveSum +
   // duplicateWithKeys offsets, rasterizer_impl.cu:280-300)
-  for_each_tile(x0, y0, x1, y1, a.gx, [&](int tile, unsigned) { atomicAdd(&im.tile_count[tile], 1u); });
+  const int T = a.gx * a.gy, warp_base = idx - (int)(threadIdx.x & 31);
+  for_each_tile(x0, y0, x1, y1, a.gx, [&](int tile, unsigned src) {
+    atomicAdd(&im.tile_count[subbin_of(warp_base + (int)src) * T + tile], 1u);
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,7 +303,12 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
   const float dcon_x = g1.w, dcon_y = g2.x, dcon_w = g2.y;
 
   a.dL_dmean2D[3 * idx] = dm2x; a.dL_dmean2D[3 * idx + 1] = dm2y; a.dL_dmean2D[3 * idx + 2] = 0.f;
-  a.dL_dopacity[idx] = dL_dopac;
+  if (a.fused) {
+    const float so = act_sigmoid(a.opacities_raw[idx]);
+    a.dL_dopacity[idx] = dL_dopac * so * (1.0f - so);  // through sigmoid
+  } else {
+    a.dL_dopacity[idx] = dL_dopac;
+  }
   a.dL_dcolor[3 * idx] = dL_dcolor[0]; a.dL_dcolor[3 * idx + 1] = dL_dcolor[1]; a.dL_dcolor[3 * idx + 2] = dL_dcolor[2];
   if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
   if (a.dL_ddepth) a.dL_ddepth[idx] = dL_ddepth;
@@ -305,7 +317,15 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
   float dcv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float dsc[3] = {0.f, 0.f, 0.f};
   float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* dsh = a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
+  // SH gradient destinations: one [P,M,3] tensor, or the f_dc / f_rest pair of the fused variant
+  float* dsh0 = a.fused ? a.dL_df_dc + (size_t)idx * 3 : (a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr);
+  float* dshr = a.fused ? a.dL_df_rest + (size_t)idx * (M - 1) * 3 : (dsh0 ? dsh0 + 3 : nullptr);
+  auto dsh_zero = [&](int from) {
+    if (!dsh0) return;
+    if (from == 0) { dsh0[0] = 0.f; dsh0[1] = 0.f; dsh0[2] = 0.f; from = 1; }
+    for (int k = from; k < M; k++) { dshr[3 * (k - 1)] = 0.f; dshr[3 * (k - 1) + 1] = 0.f; dshr[3 * (k - 1) + 2] = 0.f; }
+  };
+  const bool have_sh = a.fused || a.shs != nullptr;
 
   if (vis) {
     const V3 mean = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
@@ -371,9 +391,10 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
     dmean[1] += (vm[6] - vm[7] * mul3) * dL_ddepth;
     dmean[2] += (vm[10] - vm[11] * mul3) * dL_ddepth;
 
-    if (a.shs) {
+    if (have_sh) {
       // SH backward, backward.cu:20-139
-      const float* sh = a.shs + (size_t)idx * M * 3;
+      const float* sh0 = a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * M * 3;
+      const float* shr = a.fused ? a.f_rest + (size_t)idx * (M - 1) * 3 : sh0 + 3;
       const float ox = mean.x - a.campos[0], oy = mean.y - a.campos[1], oz = mean.z - a.campos[2];
       const float len = sqrt(ox * ox + oy * oy + oz * oz);
       const float x = ox / len, y = oy / len, z = oz / len;
@@ -384,8 +405,10 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
       float ddx = 0.f, ddy = 0.f, ddz = 0.f;
       auto emit = [&](int k, float w, float bx, float by, float bz) {
         // dL_dsh[k] = w * dRGB ; d(dir) += d(basis_k)/d(dir) * dot(sh[k], dRGB)
-        const float s = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
-        dsh[3 * k] = w * dRGB[0]; dsh[3 * k + 1] = w * dRGB[1]; dsh[3 * k + 2] = w * dRGB[2];
+        const float* shk = k == 0 ? sh0 : shr + 3 * (k - 1);
+        float* dk = k == 0 ? dsh0 : dshr + 3 * (k - 1);
+        const float s = shk[0] * dRGB[0] + shk[1] * dRGB[1] + shk[2] * dRGB[2];
+        dk[0] = w * dRGB[0]; dk[1] = w * dRGB[1]; dk[2] = w * dRGB[2];
         ddx += bx * s; ddy += by * s; ddz += bz * s;
       };
       emit(0, kC0, 0.f, 0.f, 0.f);
@@ -415,7 +438,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
           }
         }
       }
-      for (int k = used; k < M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+      dsh_zero(used);
       // dnormvdv (auxiliary.h:107-117)
       const float sum2 = ox * ox + oy * oy + oz * oz;
       const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
@@ -426,11 +449,12 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
 
     if (a.scales) {
       // cov3D backward, backward.cu:278-341 (gradient w.r.t. the un-normalised quaternion)
-      const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+      float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+      float as0 = a.scales[3 * idx], as1 = a.scales[3 * idx + 1], as2 = a.scales[3 * idx + 2];
+      if (a.fused) { q = act_normalize(q); as0 = expf(as0); as1 = expf(as1); as2 = expf(as2); }
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       const Mat3 R = quat_mat(r, x, y, z);
-      const float sx = a.scale_modifier * a.scales[3 * idx], sy = a.scale_modifier * a.scales[3 * idx + 1],
-                  sz = a.scale_modifier * a.scales[3 * idx + 2];
+      const float sx = a.scale_modifier * as0, sy = a.scale_modifier * as1, sz = a.scale_modifier * as2;
       const Mat3 Mm = mmul(scale_mat(sx, sy, sz), R);
       Mat3 dSg;
       dSg.m[0][0] = dcv[0]; dSg.m[0][1] = 0.5f * dcv[1]; dSg.m[0][2] = 0.5f * dcv[2];
@@ -453,13 +477,20 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
       dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
       dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
       dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+      if (a.fused) {
+        // chain through exp (scale) and F.normalize (rotation): d/dq_raw = (g - qhat (qhat . g)) / |q_raw|
+        dsc[0] *= as0; dsc[1] *= as1; dsc[2] *= as2;
+        float inv_n;
+        act_normalize(reinterpret_cast<const float4*>(a.rotations)[idx], &inv_n);
+        const float dot = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w;
+        dq = make_float4((dq.x - q.x * dot) * inv_n, (dq.y - q.y * dot) * inv_n, (dq.z - q.z * dot) * inv_n,
+                         (dq.w - q.w * dot) * inv_n);
+      }
     }
-  } else if (dsh) {
-    for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+  } else {
+    dsh_zero(0);
   }
-  if (vis && dsh && !a.shs) {
-    for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
-  }
+  if (vis && !have_sh) dsh_zero(0);
   a.dL_dmean3D[3 * idx] = dmean[0]; a.dL_dmean3D[3 * idx + 1] = dmean[1]; a.dL_dmean3D[3 * idx + 2] = dmean[2];
 #pragma unroll
   for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * idx + k] = dcv[k];

@@ -75,6 +75,43 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_cov3Ds_precomp, None)
 
 
+class _RasterizeGaussiansFused(torch.autograd.Function):
+    """Fused-activation variant: inputs are the model's RAW attributes; exp / sigmoid /
+    normalize / cat(f_dc, f_rest) of `VanillaRenderer.get_gaussians_properties`
+    (gaustudio/renderers/vanilla_renderer.py:28-52) happen inside the projection kernel and its backward."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, f_dc, f_rest, opacity_logits, log_scales, raw_rotations, raster_settings):
+        rs = raster_settings
+        e = torch.Tensor([])
+        out = _C.rasterize_gaussians(rs.bg, means3D, e, opacity_logits, log_scales, raw_rotations, rs.scale_modifier, e,
+                                     rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                                     rs.image_width, e, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug,
+                                     _fused=(f_dc, f_rest))
+        num_rendered, color, depth, median_depth, final_opacity, radii, geomBuffer, binningBuffer, imgBuffer = out
+        ctx.raster_settings, ctx.num_rendered = rs, num_rendered
+        ctx.save_for_backward(means3D, f_dc, f_rest, opacity_logits, log_scales, raw_rotations, radii, geomBuffer,
+                              binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, median_depth, final_opacity
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth, grad_median_depth, grad_final_opacity):
+        rs = ctx.raster_settings
+        means3D, f_dc, f_rest, opac, scales, rots, radii, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
+        d_m2, d_op, d_m3, d_dc, d_rest, d_sc, d_rot = _C.rasterize_gaussians_fused_backward(
+            rs.bg, means3D, radii, f_dc, f_rest, opac, scales, rots, rs.scale_modifier, rs.viewmatrix, rs.projmatrix,
+            rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, grad_median_depth, grad_final_opacity, rs.sh_degree,
+            rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.debug)
+        return d_m3, d_m2, d_dc, d_rest, d_op, d_sc, d_rot, None
+
+
+def rasterize_gaussians_fused(means3D, means2D, f_dc, f_rest, opacity_logits, log_scales, raw_rotations,
+                              raster_settings):
+    return _RasterizeGaussiansFused.apply(means3D, means2D, f_dc, f_rest, opacity_logits, log_scales, raw_rotations,
+                                          raster_settings)
+
+
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
     image_width: int

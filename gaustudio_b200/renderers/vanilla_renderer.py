@@ -41,6 +41,9 @@ class VanillaRenderer(BaseRenderer):
         'convert_SHs_python': False,
         'compute_cov3D_python': False,
         'debug': False,
+        # B200 extension (off by default = the reference's op sequence): apply exp / sigmoid / normalize /
+        # cat(f_dc, f_rest) inside the projection kernel instead of as per-view torch ops
+        'fused_activations': False,
     }
 
     def __init__(self, config) -> None:
@@ -54,6 +57,41 @@ class VanillaRenderer(BaseRenderer):
         self.convert_SHs_python = self.config['convert_SHs_python']
         self.compute_cov3D_python = self.config['compute_cov3D_python']
         self.debug = self.config['debug']
+        self.fused_activations = self.config['fused_activations']
+
+    _DEFAULT_ACT = {"scale": "exp", "opacity": "sigmoid", "rot": "normalize"}
+
+    def _can_fuse(self, m):
+        if not self.fused_activations or self.convert_SHs_python or self.compute_cov3D_python:
+            return False
+        if not all(hasattr(m, a) for a in ("_xyz", "_scale", "_rot", "_opacity", "_f_dc", "_f_rest")):
+            return False
+        cfg = getattr(m, "config", None)
+        if isinstance(cfg, dict) and "activations" in cfg and dict(cfg["activations"]) != self._DEFAULT_ACT:
+            return False
+        return m._scale.shape[-1] == 3 and m._f_rest.numel() > 0
+
+    def render(self, viewpoint_camera, gaussian_model):
+        if not self._can_fuse(gaussian_model):
+            return super().render(viewpoint_camera, gaussian_model)
+        import math
+        from ..rasterizer import GaussianRasterizationSettings, rasterize_gaussians_fused
+        m = gaussian_model
+        xyz = m._xyz
+        screenspace_points = torch.zeros_like(xyz, requires_grad=True)
+        rs = GaussianRasterizationSettings(
+            int(viewpoint_camera.image_height), int(viewpoint_camera.image_width),
+            math.tan(viewpoint_camera.FoVx * 0.5), math.tan(viewpoint_camera.FoVy * 0.5), self.bg_color,
+            self.scaling_modifier, viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform,
+            m.active_sh_degree, viewpoint_camera.camera_center, False, self.debug)
+        P = xyz.shape[0]
+        image, radii, depth, median_map, opacity = rasterize_gaussians_fused(
+            xyz, screenspace_points, m._f_dc.reshape(P, -1, 3), m._f_rest.reshape(P, -1, 3), m._opacity, m._scale,
+            m._rot, rs)
+        return {"render": image, "rendered_depth": depth, "rendered_median_depth": median_map[0:1],
+                "rendered_median_weight": median_map[1:2], "rendered_median_id": median_map[2:3].int(),
+                "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+                "rendered_final_opacity": opacity, "radii": radii}
 
     def get_gaussians_properties(self, viewpoint_camera, gaussian_model):
         xyz = gaussian_model.get_attribute("xyz")

@@ -76,6 +76,33 @@ int gsr_backward(int P, int D, int M, int64_t R, const float* background, int wi
                  float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
                  float* dL_dscale, float* dL_drot, int debug, void* stream);
 
+/* Fused-activation variants -- the step immediately before the path in every caller:
+ * gaustudio's VanillaRenderer.get_gaussians_properties (gaustudio/renderers/vanilla_renderer.py:28-52) runs
+ * exp(_scale), sigmoid(_opacity), normalize(_rot) and cat(_f_dc, _f_rest) as separate elementwise kernels on
+ * every view (gaustudio/models/vanilla_sg.py:58-63,102-106; models/utils.py:6-32).  These entry points take the
+ * model's RAW attributes instead -- log_scales[P,3], raw_rotations[P,4], opacity_logits[P], f_dc[P,1,3],
+ * f_rest[P,M-1,3] -- and apply the activations inside the projection kernel; the backward returns gradients
+ * w.r.t. the raw attributes (dL_dlog_scale, dL_draw_rot, dL_dopacity_logit, dL_df_dc, dL_df_rest).  Everything
+ * else is identical to gsr_forward / gsr_backward; the opaque buffers are interchangeable. */
+int64_t gsr_forward_fused(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc,
+                          void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
+                          const float* background, int width, int height, const float* means3D, const float* f_dc,
+                          const float* f_rest, const float* opacity_logits, const float* log_scales,
+                          float scale_modifier, const float* raw_rotations, const float* viewmatrix,
+                          const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                          int prefiltered, float* out_color, float* out_depth, float* out_median_depth,
+                          float* out_opacity, int* radii, int debug, int64_t r_capacity, int64_t* r_host,
+                          void* stream);
+int gsr_backward_fused(int P, int D, int M, int64_t R, const float* background, int width, int height,
+                       const float* means3D, const float* f_dc, const float* f_rest, const float* opacity_logits,
+                       const float* log_scales, float scale_modifier, const float* raw_rotations,
+                       const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                       float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                       const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dpix_median_depth,
+                       const float* dL_dpix_final_opacity, float* dL_dmean2D, float* dL_dopacity_logit,
+                       float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_df_dc, float* dL_df_rest,
+                       float* dL_dlog_scale, float* dL_draw_rot, int debug, void* stream);
+
 /* Replaces Rasterizer::markVisible (rasterizer.h:27-32, impl rasterizer_impl.cu:54-66,141-153).
  * present: device bool[P] (1 byte each). */
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -7,7 +7,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 model, cams, c = build_config(name, K=8)
 dev = torch.device("cuda"); model.to(dev).requires_grad_(True)
-r = renderers.make("vanilla_renderer")
+r = renderers.make({"name": "vanilla_renderer", "fused_activations": True})
 for i in range(steps):
     cam = cams[i].to(dev)
     out = r.render(cam, model)
