@@ -9,15 +9,17 @@
 //            (depth bits << 32 | gaussian index) per touched tile through per-tile write cursors.  Counters
 //            and cursors are split into SUBBINS per tile so the returning atomics do not serialise on one
 //            L2 address for a crowded tile;
-//   level 2  each tile's segment is radix-sorted by one CTA -- in shared memory when it fits, in place in
-//            global memory (L2-resident) otherwise -- and the sorted order is materialised as a contiguous
-//            slab of 48-byte splat records, which is what the render kernels stream with TMA bulk copies.
+//   level 2  each tile's segment is sorted by one CTA (MSD split into depth buckets + one warp-level bitonic
+//            network per bucket) -- in shared memory when it fits, in global memory (L2-resident) otherwise --
+//            and the sorted order is materialised as a contiguous slab of 48-byte splat records, which is what
+//            the render kernels stream with TMA bulk copies.
 // Order parity: the reference's sort is stable and its emit order is ascending Gaussian index
 // (rasterizer_impl.cu:98-108), so "stable by (tile, depth bits)" == total order by
-// (tile, depth bits, gaussian index).  Level 2 sorts by depth bits with a stable LSD radix sort and, only if
-// it then finds equal-depth neighbours out of index order, redoes the sort over the full 64-bit entry; the
-// result never depends on the (non-deterministic) arrival order of the level-1 scatter.
+// (tile, depth bits, gaussian index).  Level 2 compares whole 64-bit entries, so the result never depends on
+// the (non-deterministic) arrival order of the level-1 scatter.
 #include "gsr_internal.cuh"
+
+#include <cstdlib>
 
 namespace gsr {
 
@@ -106,190 +108,154 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
 }
 
 // ---- level 2: per-tile sort + slab gather ---------------------------------------------------------
-constexpr int SORT_THREADS = 256;
+// One CTA per tile.  An MSD split on the 8 highest *varying* bits of the depth key partitions the tile's
+// entries into up to 256 depth buckets (shared-memory atomics: the split need not be stable), then every
+// bucket -- a few dozen entries -- is sorted by one warp with a shuffle bitonic network on the full 64-bit
+// entry (depth bits << 32 | gaussian index).  Comparing the whole entry yields the reference's order
+// (stable by depth == ties in ascending Gaussian index) with no dependence on the scatter's arrival order.
+constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_CAP = 4096;       // entries per buffer kept in shared memory (2 x 32 KB)
-constexpr int SMALL_N = 256;         // up to here a bitonic network in shared memory is cheaper
-constexpr size_t SORT_SMEM = 2 * SORT_CAP * sizeof(unsigned long long);
+constexpr int SORT_CAP = 8192;  // entries sorted in shared memory (64 KB); larger tiles use global
+constexpr size_t SORT_SMEM = SORT_CAP * sizeof(unsigned long long);
+typedef unsigned long long u64;
 
-// Bitonic network in its "all ascending" form (first step of every merge mirrors the partner index), which
-// tolerates an arbitrary n by treating indices >= n as +inf: such pairs never swap, so they are skipped.
-__device__ __forceinline__ void bitonic_small(unsigned long long* k, unsigned n) {
-  unsigned npad = 1;
-  while (npad < n) npad <<= 1;
+// ascending bitonic sort of one key per lane (unused lanes hold ~0ull)
+__device__ __forceinline__ u64 warp_sort32(u64 key, unsigned lane) {
+#pragma unroll
+  for (unsigned k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      const u64 other = __shfl_xor_sync(FULL, key, j);
+      const bool up = (lane & k) == 0 || k == 32;
+      const bool lower = (lane & j) == 0;
+      const u64 mn = key < other ? key : other, mx = key < other ? other : key;
+      key = (lower == up) ? mn : mx;
+    }
+  }
+  return key;
+}
+
+// one warp sorts k[0,m) in place (shared or global memory), m > 32: "all ascending" bitonic network, where
+// indices >= m behave as +inf (such pairs never swap and are skipped)
+__device__ __forceinline__ void warp_sort_mem(u64* k, unsigned m, unsigned lane) {
+  unsigned npad = 64;
+  while (npad < m) npad <<= 1;
   const unsigned half = npad >> 1;
   for (unsigned blk = 2; blk <= npad; blk <<= 1) {
     const unsigned hb = blk >> 1;
-    for (unsigned t = threadIdx.x; t < half; t += SORT_THREADS) {
-      const unsigned base = (t / hb) * blk, off = t % hb;
-      const unsigned i = base + off, p = base + blk - 1 - off;
-      if (p < n) { const unsigned long long a = k[i], c = k[p]; if (a > c) { k[i] = c; k[p] = a; } }
+    for (unsigned t = lane; t < half; t += 32) {
+      const unsigned base = (t / hb) * blk, off = t % hb, i = base + off, p = base + blk - 1 - off;
+      if (p < m) { const u64 a = k[i], c = k[p]; if (a > c) { k[i] = c; k[p] = a; } }
     }
-    __syncthreads();
+    __syncwarp();
     for (unsigned j = blk >> 2; j > 0; j >>= 1) {
-      for (unsigned t = threadIdx.x; t < half; t += SORT_THREADS) {
+      for (unsigned t = lane; t < half; t += 32) {
         const unsigned i = 2 * j * (t / j) + (t % j), p = i + j;
-        if (p < n) { const unsigned long long a = k[i], c = k[p]; if (a > c) { k[i] = c; k[p] = a; } }
+        if (p < m) { const u64 a = k[i], c = k[p]; if (a > c) { k[i] = c; k[p] = a; } }
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
 }
 
-struct RadixShared {
-  unsigned hw[SORT_WARPS][256];  // per-warp digit counts, then running write offsets
-  unsigned tot[256];
-  unsigned wsum[SORT_WARPS];
-  unsigned flag;
+struct SortShared {
+  unsigned cnt[256];
+  unsigned start[257];
+  unsigned wsum[8];
+  unsigned diff;
 };
 
-// Lanes of `act` holding the same 8-bit digit (what __match_any_sync returns), built from 8 ballots:
-// MATCH.ANY goes through the MIO pipe with a long latency on sm_100, VOTE does not.
-__device__ __forceinline__ unsigned match_digit(unsigned act, unsigned d) {
-  unsigned peers = act;
-#pragma unroll
-  for (int b = 0; b < 8; b++) {
-    const bool bit = (d >> b) & 1u;
-    const unsigned m = __ballot_sync(act, bit);
-    peers &= bit ? m : ~m;
-  }
-  return peers;
-}
-
-// One stable LSD pass on the byte at bit `shift` of the 64-bit entries: src[0,n) -> dst[0,n).
-// Warp w owns the contiguous chunk [w*m, (w+1)*m); stability = (chunk, position).  Ranks inside a 32-entry
-// round come from ballots (match_digit), so no per-element atomics are needed.
-__device__ __forceinline__ void radix_pass(const unsigned long long* src, unsigned long long* dst, unsigned n,
-                                           unsigned shift, RadixShared& sh) {
-  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned m = (n + SORT_WARPS - 1) / SORT_WARPS;
-  const unsigned beg = min(n, warp * m), end = min(n, beg + m);
-  for (unsigned i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&sh.hw[0][0])[i] = 0;
-  __syncthreads();
-  for (unsigned base = beg; base < end; base += 32) {
-    const unsigned i = base + lane;
-    const bool valid = i < end;
-    const unsigned act = __ballot_sync(FULL, valid);
-    if (valid) {
-      const unsigned d = (unsigned)(src[i] >> shift) & 255u;
-      const unsigned peers = match_digit(act, d);
-      if ((peers & ((1u << lane) - 1)) == 0) sh.hw[warp][d] += __popc(peers);  // leader of each digit group
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  // offsets: digit-major, warp-minor exclusive scan of hw[w][d]
-  {
-    const unsigned d = tid;  // SORT_THREADS == 256 digits
-    unsigned run = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) { const unsigned c = sh.hw[w][d]; sh.hw[w][d] = run; run += c; }
-    unsigned v = run;  // total of digit d; block exclusive scan over d
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
-    if (lane == 31) sh.wsum[warp] = v;
-    __syncthreads();
-    unsigned basew = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) basew += (w < (int)warp) ? sh.wsum[w] : 0u;
-    sh.tot[d] = basew + v - run;
-  }
-  __syncthreads();
-  for (unsigned base = beg; base < end; base += 32) {
-    const unsigned i = base + lane;
-    const bool valid = i < end;
-    const unsigned act = __ballot_sync(FULL, valid);
-    unsigned long long key = 0;
-    unsigned d = 0, peers = 0, pos = 0;
-    if (valid) {
-      key = src[i];
-      d = (unsigned)(key >> shift) & 255u;
-      peers = match_digit(act, d);
-      pos = sh.tot[d] + sh.hw[warp][d] + __popc(peers & ((1u << lane) - 1));
-    }
-    __syncwarp();
-    if (valid) {
-      if ((peers & ((1u << lane) - 1)) == 0) sh.hw[warp][d] += __popc(peers);
-      dst[pos] = key;
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-}
-
-// Sorts bits [lo, lo+32) of the entries with as many byte passes as there are non-constant bytes.
-// Returns the buffer holding the result (a or b).
-__device__ __forceinline__ unsigned long long* radix_field(unsigned long long* a, unsigned long long* b, unsigned n,
-                                                           unsigned lo, RadixShared& sh) {
-  // which bytes vary inside this tile?  (depths in one tile usually share sign/exponent bytes)
-  if (threadIdx.x == 0) sh.flag = 0;
-  __syncthreads();
-  const unsigned first = (unsigned)(a[0] >> lo);
-  unsigned diff = 0;
-  for (unsigned i = threadIdx.x; i < n; i += SORT_THREADS) diff |= (unsigned)(a[i] >> lo) ^ first;
-  diff = __reduce_or_sync(FULL, diff);
-  if ((threadIdx.x & 31) == 0 && diff) atomicOr(&sh.flag, diff);
-  __syncthreads();
-  diff = sh.flag;
-  __syncthreads();
-  for (unsigned byte = 0; byte < 4; byte++) {
-    if (((diff >> (8 * byte)) & 255u) == 0) continue;
-    radix_pass(a, b, n, lo + 8 * byte, sh);
-    unsigned long long* t = a; a = b; b = t;
-  }
-  return a;
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b) {
-  extern __shared__ __align__(16) unsigned long long sort_smem[];
-  __shared__ RadixShared sh;
+__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b, int dbg_mode) {
+  extern __shared__ __align__(16) u64 sort_smem[];
+  __shared__ SortShared sh;
   const uint2 range = im.tile_range[blockIdx.x];
   const unsigned n = range.y - range.x;
   if (n == 0) return;
-  unsigned long long* seg = b.ents + range.x;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64* seg = b.ents + range.x;
   float4* out = b.slab + (size_t)range.x * SPLAT_F4;
-  unsigned long long *A, *B;
-  if (n <= SORT_CAP) {
-    A = sort_smem; B = sort_smem + SORT_CAP;
-    for (unsigned i = threadIdx.x; i < n; i += SORT_THREADS) A[i] = seg[i];
-    __syncthreads();
-  } else {
-    // rare: more instances than fit in shared memory.  Ping-pong between the entry segment and the tile's
-    // (not yet written) slab region, both L2-resident.
-    A = seg; B = reinterpret_cast<unsigned long long*>(out);
-    __syncthreads();
-  }
-  const unsigned long long* sorted;
-  if (n <= SMALL_N) {
-    bitonic_small(A, n);
-    sorted = A;
-  } else {
-    unsigned long long* r = radix_field(A, B, n, 32, sh);
-    // equal depth bits must come in ascending Gaussian index (stable-sort parity); arrival order is arbitrary
-    unsigned bad = 0;
-    for (unsigned i = threadIdx.x + 1; i < n; i += SORT_THREADS) bad |= (r[i] < r[i - 1]);
-    if (__syncthreads_or(bad)) {
-      unsigned long long* o = (r == A) ? B : A;
-      r = radix_field(r, o, n, 0, sh);
-      o = (r == A) ? B : A;
-      r = radix_field(r, o, n, 32, sh);
+  const u64* sorted;
+
+  if (dbg_mode == 1) {
+    sorted = seg;  // timing experiment: no sort
+  } else if (n <= 32) {
+    // a single warp sorts the whole tile in registers
+    if (warp == 0) {
+      const u64 key = warp_sort32(lane < n ? seg[lane] : ~0ull, lane);
+      if (lane < n) sort_smem[lane] = key;
     }
-    sorted = r;
-  }
-  if (n > SORT_CAP && sorted != seg) {
-    // the result sits in the slab region that the gather below overwrites: move it back first
-    for (unsigned i = threadIdx.x; i < n; i += SORT_THREADS) seg[i] = sorted[i];
     __syncthreads();
-    sorted = seg;
+    sorted = sort_smem;
+  } else {
+    const bool in_smem = n <= SORT_CAP;
+    // A: unsorted input, B: bucketed + sorted output.  Large tiles ping-pong between the entry segment and the
+    // tile's (not yet written) slab region, both L2-resident.
+    const u64* A = seg;
+    u64* B = in_smem ? sort_smem : reinterpret_cast<u64*>(out);
+    if (tid < 256) sh.cnt[tid] = 0;
+    if (tid == 0) sh.diff = 0;
+    __syncthreads();
+    // digit = the 8 highest depth bits that are not identical across the tile
+    const unsigned first = (unsigned)(A[0] >> 32);
+    unsigned diff = 0;
+    for (unsigned i = tid; i < n; i += SORT_THREADS) diff |= (unsigned)(A[i] >> 32) ^ first;
+    diff = __reduce_or_sync(FULL, diff);
+    if (lane == 0 && diff) atomicOr(&sh.diff, diff);
+    __syncthreads();
+    diff = sh.diff;
+    const unsigned shift = 32u + (diff ? (unsigned)max(0, 31 - __clz((int)diff) - 7) : 0u);
+    for (unsigned i = tid; i < n; i += SORT_THREADS) atomicAdd(&sh.cnt[(unsigned)(A[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (tid < 256) {  // exclusive scan of the 256 bucket sizes
+      const unsigned c = sh.cnt[tid];
+      unsigned v = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
+      if (lane == 31) sh.wsum[warp] = v;
+      __syncwarp();
+      // the 8 participating warps synchronise through a named barrier (the other 8 skip this block)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      unsigned basew = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) basew += (w < (int)warp) ? sh.wsum[w] : 0u;
+      sh.start[tid] = basew + v - c;
+      sh.cnt[tid] = basew + v - c;  // running cursor for the split
+      if (tid == 255) sh.start[256] = basew + v;
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < n; i += SORT_THREADS) {
+      const u64 key = A[i];
+      B[atomicAdd(&sh.cnt[(unsigned)(key >> shift) & 255u], 1u)] = key;
+    }
+    __syncthreads();
+    for (unsigned bk = warp; bk < 256; bk += SORT_WARPS) {
+      const unsigned s0 = sh.start[bk], m = sh.start[bk + 1] - s0;
+      if (m <= 1) continue;
+      if (m <= 32) {
+        const u64 key = warp_sort32(lane < m ? B[s0 + lane] : ~0ull, lane);
+        if (lane < m) B[s0 + lane] = key;
+      } else {
+        warp_sort_mem(B + s0, m, lane);
+      }
+    }
+    __syncthreads();
+    if (!in_smem) {
+      // the result sits in the slab region that the gather below overwrites: move it to the entry segment
+      for (unsigned i = tid; i < n; i += SORT_THREADS) seg[i] = B[i];
+      __syncthreads();
+      sorted = seg;
+    } else {
+      sorted = B;
+    }
   }
   // gather the splat records in sorted order into the tile's contiguous slab
-  for (unsigned i = threadIdx.x; i < n; i += SORT_THREADS) {
-    const unsigned id = (unsigned)sorted[i];
-    const float4* s = g.splat + (size_t)id * SPLAT_F4;
-    const float4 q0 = s[0], q1 = s[1], q2 = s[2];
-    out[(size_t)i * SPLAT_F4 + 0] = q0;
-    out[(size_t)i * SPLAT_F4 + 1] = q1;
-    out[(size_t)i * SPLAT_F4 + 2] = q2;
+  if (dbg_mode == 2) return;  // timing experiment: no gather
+  // (three consecutive lanes move the three 16-byte pieces of one record: loads of a record share its two
+  // sectors and every warp store is one contiguous 512-byte run of the slab)
+  for (unsigned c = tid; c < 3 * n; c += SORT_THREADS) {
+    const unsigned rec = c / 3, part = c - 3 * rec;
+    const unsigned id = (unsigned)sorted[rec];
+    out[c] = g.splat[(size_t)id * SPLAT_F4 + part];
   }
 }
 
@@ -303,7 +269,8 @@ void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, c
 
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
   cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM);  // per device
-  k_tile_sort<<<T, SORT_THREADS, SORT_SMEM, st>>>(g, im, b);
+  static const int dbg_mode = getenv("GSR_SORT_DEBUG") ? atoi(getenv("GSR_SORT_DEBUG")) : 0;  // timing experiments only
+  k_tile_sort<<<T, SORT_THREADS, SORT_SMEM, st>>>(g, im, b, dbg_mode);
 }
 
 }  // namespace gsr

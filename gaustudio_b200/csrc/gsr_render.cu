@@ -24,8 +24,11 @@ namespace gsr {
 
 namespace {
 
-constexpr int RB = 256;                       // records per pipeline stage
-constexpr int STAGE_F4 = RB * SPLAT_F4;       // float4 per stage (12 KB)
+constexpr int RB = 128;                       // records per pipeline stage
+constexpr int NSTAGE = 4;                     // ring depth: consumer warps may drift this many batches apart
+constexpr int STAGE_F4 = RB * SPLAT_F4;       // float4 per stage (6 KB)
+constexpr int NCONS = TILE_PIX / 32;          // 8 consumer warps (one 8x4 sub-tile each) + 1 producer warp
+constexpr int RENDER_THREADS = TILE_PIX + 32;
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -44,6 +47,22 @@ __device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(b)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned b = smem_u32(bar);
@@ -92,20 +111,73 @@ __device__ __forceinline__ bool may_touch(const float4 q0, const float4 q1, floa
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory ring shared by both kernels: NSTAGE slab batches, `full` barriers completed by the TMA
+// transaction count, `empty` barriers by one arrival per consumer warp.  Warp NCONS (the 9th) is the
+// producer: one elected lane re-arms a stage and issues the bulk copy as soon as every consumer released it.
+// Consumer warps never meet at a CTA-wide barrier inside the loop, so a sub-tile with little work does not
+// wait for a crowded one batch by batch.
+// ---------------------------------------------------------------------------------------------
+struct Ring {
+  float4 buf[NSTAGE][STAGE_F4];
+  unsigned long long full[NSTAGE];
+  unsigned long long empty[NSTAGE];
+  unsigned ndone;           // consumer warps that have no pixel left (forward early exit)
+  unsigned maxc[NCONS];
+};
+
+__device__ __forceinline__ void ring_init(Ring& r) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(&r.full[s], 1); mbar_init(&r.empty[s], NCONS); }
+    r.ndone = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_PIX) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
-                                                         float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                         float* __restrict__ out_median, float* __restrict__ out_opacity) {
-  __shared__ __align__(128) float4 sbuf[2][STAGE_F4];
-  __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ unsigned s_maxc[TILE_PIX / 32];
-
+__global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
+                                                               float* __restrict__ out_color,
+                                                               float* __restrict__ out_depth,
+                                                               float* __restrict__ out_median,
+                                                               float* __restrict__ out_opacity) {
+  __shared__ __align__(128) Ring ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
   const uint2 range = im.tile_range[tile];
   const int n = (int)(range.y - range.x);
-  // warp w owns the 8x4 sub-tile at (w&1, w>>1)
+  const int nb = (n + RB - 1) / RB;
+  const float4* slab = bin.slab + (size_t)range.x * SPLAT_F4;
+  ring_init(ring);
+
+  if (warp == NCONS) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      int issued = 0;
+      for (int b = 0; b < nb; b++) {
+        const int s = b % NSTAGE;
+        if (b >= NSTAGE) {
+          const unsigned par = (unsigned)((b / NSTAGE - 1) & 1);
+          bool stop = false;
+          while (!mbar_try(&ring.empty[s], par)) {
+            if (*(volatile unsigned*)&ring.ndone == NCONS) { stop = true; break; }
+          }
+          if (stop) break;
+        }
+        if (*(volatile unsigned*)&ring.ndone == NCONS) break;
+        const int cnt = min(RB, n - b * RB);
+        tma_load(ring.buf[s], slab + (size_t)b * STAGE_F4, (unsigned)cnt * SPLAT_BYTES, &ring.full[s]);
+        issued = b + 1;
+      }
+      // every bulk copy must have landed before the CTA's shared memory is released
+      for (int b = max(0, issued - NSTAGE); b < issued; b++) mbar_wait(&ring.full[b % NSTAGE], (unsigned)((b / NSTAGE) & 1));
+    }
+    return;
+  }
+
+  // ---------------- consumers: warp w owns the 8x4 sub-tile at (w&1, w>>1) ----------------
   const int sx0 = tx * TILE_X + (warp & 1) * 8, sy0 = ty * TILE_Y + (warp >> 1) * 4;
   const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
   const bool inside = px < W && py < H;
@@ -117,75 +189,68 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_fwd(int W, int H, int gx, I
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
   float med_d = 15.0f, med_w = 0.f, med_id = 0.f;  // forward.cu:310-312
   unsigned last_contributor = 0;
-
-  const int nb = (n + RB - 1) / RB;
-  const float4* slab = bin.slab + (size_t)range.x * SPLAT_F4;
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0 && nb > 0) tma_load(sbuf[0], slab, (unsigned)min(RB, n) * SPLAT_BYTES, &mbar[0]);
-
   bool warp_done = __all_sync(FULL, done);
-  int b = 0;
-  bool prefetched = false;
-  for (; b < nb; b++) {
-    const int stage = b & 1;
-    prefetched = false;
-    if (tid == 0 && b + 1 < nb) {
-      const int cnt1 = min(RB, n - (b + 1) * RB);
-      tma_load(sbuf[stage ^ 1], slab + (size_t)(b + 1) * STAGE_F4, (unsigned)cnt1 * SPLAT_BYTES, &mbar[stage ^ 1]);
-      prefetched = true;
-    }
-    mbar_wait(&mbar[stage], (unsigned)(b >> 1) & 1u);
-    const int cnt = min(RB, n - b * RB);
-    const float4* sb = sbuf[stage];
-    if (!warp_done) {
-      for (int base = 0; base < cnt; base += 32) {
-        const int j = base + lane;
-        bool keep = false;
-        if (j < cnt) keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
-        unsigned mask = __ballot_sync(FULL, keep);
-        while (mask) {
-          const int jj = base + __ffs(mask) - 1;
-          mask &= mask - 1;
-          if (done) continue;
-          const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
-          // forward.cu:343-356 with the contraction of the reference SASS
-          const float dx = q0.x - pxf, dy = q0.y - pyf;
-          const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
-          const float t2 = __fmul_rn(dx, q0.z);
-          const float t3 = __fmul_rn(__fmul_rn(dx, q0.w), dy);
-          const float power = __fmaf_rn(__fmaf_rn(dx, t2, t1), -0.5f, -t3);
-          if (power > 0.0f) continue;
-          const float alpha = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
-          if (alpha < 1.0f / 255.0f) continue;
-          const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-          if (test_T < 0.0001f) { done = true; continue; }
-          const float4 q2 = sb[jj * SPLAT_F4 + 2];
-          C0 = __fmaf_rn(T, __fmul_rn(alpha, q1.w), C0);
-          C1 = __fmaf_rn(T, __fmul_rn(alpha, q2.x), C1);
-          C2 = __fmaf_rn(T, __fmul_rn(alpha, q2.y), C2);
-          D = __fmaf_rn(T, __fmul_rn(alpha, q1.z), D);
-          if (T > 0.5f && test_T < 0.5f) {
-            med_d = q1.z;
-            med_w = __fmul_rn(alpha, T);
-            med_id = (float)__float_as_int(q2.z);
-          }
-          T = test_T;
-          last_contributor = (unsigned)(b * RB + jj + 1);
-        }
-        warp_done = __all_sync(FULL, done);
-        if (warp_done) break;
+  if (warp_done && lane == 0) atomicAdd(&ring.ndone, 1u);
+
+  for (int b = 0; b < nb; b++) {
+    const int s = b % NSTAGE;
+    const unsigned par = (unsigned)((b / NSTAGE) & 1);
+    if (warp_done) {
+      // nothing left for this warp: keep releasing stages until the whole tile is finished
+      bool stop = false;
+      while (!mbar_try(&ring.full[s], par)) {
+        if (*(volatile unsigned*)&ring.ndone == NCONS) { stop = true; break; }
       }
+      if (stop || *(volatile unsigned*)&ring.ndone == NCONS) break;
+      if (lane == 0) mbar_arrive(&ring.empty[s]);
+      continue;
     }
-    // everyone is finished with this stage (and, if all pixels are done, with the tile)
-    if (__syncthreads_and(warp_done)) break;
+    mbar_wait(&ring.full[s], par);
+    const int cnt = min(RB, n - b * RB);
+    const float4* sb = ring.buf[s];
+    for (int base = 0; base < cnt; base += 32) {
+      const int j = base + lane;
+      bool keep = false;
+      if (j < cnt) keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
+      unsigned mask = __ballot_sync(FULL, keep);
+      while (mask) {
+        const int jj = base + __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (done) continue;
+        const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
+        // forward.cu:343-356 with the contraction of the reference SASS
+        const float dx = q0.x - pxf, dy = q0.y - pyf;
+        const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
+        const float t2 = __fmul_rn(dx, q0.z);
+        const float t3 = __fmul_rn(__fmul_rn(dx, q0.w), dy);
+        const float power = __fmaf_rn(__fmaf_rn(dx, t2, t1), -0.5f, -t3);
+        if (power > 0.0f) continue;
+        const float alpha = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        if (test_T < 0.0001f) { done = true; continue; }
+        const float4 q2 = sb[jj * SPLAT_F4 + 2];
+        C0 = __fmaf_rn(T, __fmul_rn(alpha, q1.w), C0);
+        C1 = __fmaf_rn(T, __fmul_rn(alpha, q2.x), C1);
+        C2 = __fmaf_rn(T, __fmul_rn(alpha, q2.y), C2);
+        D = __fmaf_rn(T, __fmul_rn(alpha, q1.z), D);
+        if (T > 0.5f && test_T < 0.5f) {
+          med_d = q1.z;
+          med_w = __fmul_rn(alpha, T);
+          med_id = (float)__float_as_int(q2.z);
+        }
+        T = test_T;
+        last_contributor = (unsigned)(b * RB + jj + 1);
+      }
+      warp_done = __all_sync(FULL, done);
+      if (warp_done) break;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&ring.empty[s]);
+      if (warp_done) atomicAdd(&ring.ndone, 1u);
+    }
   }
-  // a bulk copy still in flight must land before the CTA's shared memory is released
-  if (tid == 0 && prefetched && b < nb) mbar_wait(&mbar[(b + 1) & 1], (unsigned)((b + 1) >> 1) & 1u);
 
   if (inside) {
     const size_t pid = (size_t)py * W + px, HW = (size_t)W * H;
@@ -200,13 +265,14 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_fwd(int W, int H, int gx, I
     out_median[2 * HW + pid] = med_id;
     out_opacity[pid] = 1 - T;
   }
+  // largest n_contrib of the tile bounds the backward traversal
   const unsigned wmax = __reduce_max_sync(FULL, last_contributor);
-  if (lane == 0) s_maxc[warp] = wmax;
-  __syncthreads();
+  if (lane == 0) ring.maxc[warp] = wmax;
+  asm volatile("bar.sync 1, %0;" ::"n"(TILE_PIX) : "memory");  // consumer warps only (the producer has left)
   if (tid == 0) {
     unsigned m = 0;
 #pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; w++) m = max(m, s_maxc[w]);
+    for (int w = 0; w < NCONS; w++) m = max(m, ring.maxc[w]);
     im.tile_maxc[tile] = m;
   }
 }
@@ -214,20 +280,36 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_fwd(int W, int H, int gx, I
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_PIX) k_render_bwd(int W, int H, int gx, const float* __restrict__ bg,
-                                                         ImageView im, BinView bin, float* __restrict__ grad,
-                                                         const float* __restrict__ dL_dpix,
-                                                         const float* __restrict__ dL_ddepthpix,
-                                                         const float* __restrict__ dL_dmedpix,
-                                                         const float* __restrict__ dL_dopacpix) {
-  __shared__ __align__(128) float4 sbuf[2][STAGE_F4];
-  __shared__ __align__(8) unsigned long long mbar[2];
-
+__global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int gx, const float* __restrict__ bg,
+                                                               ImageView im, BinView bin, float* __restrict__ grad,
+                                                               const float* __restrict__ dL_dpix,
+                                                               const float* __restrict__ dL_ddepthpix,
+                                                               const float* __restrict__ dL_dmedpix,
+                                                               const float* __restrict__ dL_dopacpix) {
+  __shared__ __align__(128) Ring ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
   const uint2 range = im.tile_range[tile];
   const int nmax = (int)min(im.tile_maxc[tile], range.y - range.x);
   if (nmax == 0) return;
+  const int nb = (nmax + RB - 1) / RB;
+  const float4* slab = bin.slab + (size_t)range.x * SPLAT_F4;
+  ring_init(ring);
+
+  // batch b (counted from the back) covers list positions [lo_b, hi_b), hi_b = nmax - b*RB
+  if (warp == NCONS) {
+    if (lane == 0) {
+      for (int b = 0; b < nb; b++) {
+        const int s = b % NSTAGE;
+        if (b >= NSTAGE) mbar_wait(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
+        const int hi = nmax - b * RB, lo = max(0, hi - RB);
+        tma_load(ring.buf[s], slab + (size_t)lo * SPLAT_F4, (unsigned)(hi - lo) * SPLAT_BYTES, &ring.full[s]);
+      }
+      // the consumers wait on every batch, so all copies have landed when they leave; nothing to drain
+    }
+    return;
+  }
+
   const int sx0 = tx * TILE_X + (warp & 1) * 8, sy0 = ty * TILE_Y + (warp >> 1) * 4;
   const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
   const bool inside = px < W && py < H;
@@ -248,33 +330,20 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_bwd(int W, int H, int gx, c
   }
   float bg_dot = 0.f;  // backward.cu:584-586
   bg_dot += bg[0] * gp0; bg_dot += bg[1] * gp1; bg_dot += bg[2] * gp2;
+  const float bg_term = -T_final * bg_dot;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
   float acc_d = 0.f, last_d = 0.f, acc_o = 0.f, last_o = 0.f, last_alpha = 0.f;
   const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
   const int warp_max = (int)__reduce_max_sync(FULL, (unsigned)last_contributor);
+  // which lane publishes which reduced component (see the butterfly below)
+  const bool pub = ((lane & 3) == 0) || lane == 1 || lane == 17;
+  const int slot = ((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9);
 
-  const int nb = (nmax + RB - 1) / RB;
-  const float4* slab = bin.slab + (size_t)range.x * SPLAT_F4;
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  // batch b (from the back) covers list positions [lo_b, hi_b), hi_b = nmax - b*RB
-  if (tid == 0) {
-    const int hi = nmax, lo = max(0, hi - RB);
-    tma_load(sbuf[0], slab + (size_t)lo * SPLAT_F4, (unsigned)(hi - lo) * SPLAT_BYTES, &mbar[0]);
-  }
   for (int b = 0; b < nb; b++) {
-    const int stage = b & 1;
-    if (tid == 0 && b + 1 < nb) {
-      const int hi1 = nmax - (b + 1) * RB, lo1 = max(0, hi1 - RB);
-      tma_load(sbuf[stage ^ 1], slab + (size_t)lo1 * SPLAT_F4, (unsigned)(hi1 - lo1) * SPLAT_BYTES, &mbar[stage ^ 1]);
-    }
-    mbar_wait(&mbar[stage], (unsigned)(b >> 1) & 1u);
+    const int s = b % NSTAGE;
+    mbar_wait(&ring.full[s], (unsigned)((b / NSTAGE) & 1));
     const int hi = nmax - b * RB, lo = max(0, hi - RB), cnt = hi - lo;
-    const float4* sb = sbuf[stage];
+    const float4* sb = ring.buf[s];
     if (lo < warp_max) {
       for (int base = 0; base < cnt; base += 32) {
         const int j = cnt - 1 - (base + lane);  // lane 0 = farthest entry of this chunk
@@ -284,7 +353,7 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_bwd(int W, int H, int gx, c
         while (mask) {
           const int jj = cnt - 1 - (base + __ffs(mask) - 1);
           mask &= mask - 1;
-          const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1], q2 = sb[jj * SPLAT_F4 + 2];
+          const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
           const float dx = q0.x - pxf, dy = q0.y - pyf;
           const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
           const float t2 = __fmul_rn(dx, q0.z);
@@ -295,70 +364,69 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_bwd(int W, int H, int gx, c
           // backward.cu:520-537: entries at or beyond n_contrib, power > 0 and alpha < 1/255 are skipped
           const bool valid = (lo + jj < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
           if (!__any_sync(FULL, valid)) continue;
+          const float4 q2 = sb[jj * SPLAT_F4 + 2];
           float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
           if (valid) {
-            const float test_T = T / (1.f - alpha);
+            const float inv = __frcp_rn(1.f - alpha);  // 1 - alpha >= 0.01
+            const float test_T = T * inv;
             const float w = alpha * test_T;
-            float dL_dalpha = 0.0f;
+            const float oma = 1.f - last_alpha;
+            float dL_dalpha;
             const float c0 = q1.w, c1 = q2.x, c2 = q2.y, c_d = q1.z;
-            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = c0; dL_dalpha += (c0 - acc0) * gp0; v0 = w * gp0;
-            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = c1; dL_dalpha += (c1 - acc1) * gp1; v1 = w * gp1;
-            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = c2; dL_dalpha += (c2 - acc2) * gp2; v2 = w * gp2;
-            acc_d = last_alpha * last_d + (1.f - last_alpha) * acc_d; last_d = c_d;
+            acc0 = last_alpha * lc0 + oma * acc0; lc0 = c0; dL_dalpha = (c0 - acc0) * gp0; v0 = w * gp0;
+            acc1 = last_alpha * lc1 + oma * acc1; lc1 = c1; dL_dalpha += (c1 - acc1) * gp1; v1 = w * gp1;
+            acc2 = last_alpha * lc2 + oma * acc2; lc2 = c2; dL_dalpha += (c2 - acc2) * gp2; v2 = w * gp2;
+            acc_d = last_alpha * last_d + oma * acc_d; last_d = c_d;
             dL_dalpha += (c_d - acc_d) * gD;
             v3 = w * gD;
             if (test_T > 0.5f && T < 0.5f) v3 += gMed;  // backward.cu:566-569
-            acc_o = last_alpha * last_o + (1.f - last_alpha) * acc_o; last_o = 1.f;
+            acc_o = last_alpha * last_o + oma * acc_o; last_o = 1.f;
             dL_dalpha += (1.f - acc_o) * gO;
             v4 = w * gO;  // direct term, backward.cu:575 (quirk 5)
             dL_dalpha *= test_T;
             T = test_T;
             last_alpha = alpha;
-            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+            dL_dalpha += bg_term * inv;  // (-T_final / (1 - alpha)) * bg_dot, backward.cu:584-587
             const float dL_dG = q1.y * dL_dalpha;
             const float gdx = G * dx, gdy = G * dy;
             const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
             const float dG_ddely = -gdy * q1.x - gdx * q0.w;
             v5 = dL_dG * dG_ddelx * ddelx_dx;
             v6 = dL_dG * dG_ddely * ddely_dy;
-            v7 = -0.5f * gdx * dx * dL_dG;
-            v8 = -0.5f * gdx * dy * dL_dG;
-            v9 = -0.5f * gdy * dy * dL_dG;
+            const float h = -0.5f * dL_dG;
+            v7 = h * gdx * dx;
+            v8 = h * gdx * dy;
+            v9 = h * gdy * dy;
             v4 += G * dL_dalpha;
           }
           // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
-          {
-            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-            float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
-            a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
-            a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
-            a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
-            a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
-            float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
-            b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
-            b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
-            float c = h4 ? b1 : b0;
-            c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
-            c += __shfl_xor_sync(FULL, c, 2);
-            c += __shfl_xor_sync(FULL, c, 1);
-            // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
-            float e = h16 ? v9 : v8;
-            e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
-            e += __shfl_xor_sync(FULL, e, 8);
-            e += __shfl_xor_sync(FULL, e, 4);
-            e += __shfl_xor_sync(FULL, e, 2);
-            e += __shfl_xor_sync(FULL, e, 1);
-            const int id = __float_as_int(q2.z);
-            float* dst = grad + (size_t)id * GRAD_F;
-            // accumulator slots: 0-2 colour, 3 depth, 4 opacity, 5-6 mean2D, 7-9 conic (xx, xy, yy)
-            if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), c);
-            else if (lane == 1) atomicAdd(dst + 8, e);
-            else if (lane == 17) atomicAdd(dst + 9, e);
-          }
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
+          a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
+          a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
+          a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
+          a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
+          float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
+          b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
+          b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
+          float c = h4 ? b1 : b0;
+          c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
+          c += __shfl_xor_sync(FULL, c, 2);
+          c += __shfl_xor_sync(FULL, c, 1);
+          // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
+          float e = h16 ? v9 : v8;
+          e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
+          e += __shfl_xor_sync(FULL, e, 8);
+          e += __shfl_xor_sync(FULL, e, 4);
+          e += __shfl_xor_sync(FULL, e, 2);
+          e += __shfl_xor_sync(FULL, e, 1);
+          // accumulator slots: 0-2 colour, 3 depth, 4 opacity, 5-6 mean2D, 7-9 conic (xx, xy, yy)
+          if (pub) atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 3) == 0) ? c : e);
         }
       }
     }
-    __syncthreads();  // stage may be refilled two iterations later
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[s]);
   }
 }
 
@@ -366,14 +434,14 @@ __global__ void __launch_bounds__(TILE_PIX) k_render_bwd(int W, int H, int gx, c
 
 void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, float* out_color, float* out_depth,
                        float* out_median, float* out_opacity, cudaStream_t st) {
-  k_render_fwd<<<gx * gy, TILE_PIX, 0, st>>>(W, H, gx, im, b, out_color, out_depth, out_median, out_opacity);
+  k_render_fwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, out_color, out_depth, out_median, out_opacity);
 }
 
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
                        const float* dL_dopacity, cudaStream_t st) {
-  k_render_bwd<<<gx * gy, TILE_PIX, 0, st>>>(W, H, gx, bg, im, b, g.grad, dL_dpix, dL_ddepth, dL_dmedian,
-                                            dL_dopacity);
+  k_render_bwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.grad, dL_dpix, dL_ddepth, dL_dmedian,
+                                                  dL_dopacity);
 }
 
 }  // namespace gsr
