@@ -95,12 +95,13 @@ BinView carve_binning(char* base, long long cap) {
   BinView b;
   char* p = base;
   take(p, b.ents, (size_t)cap);
-  take(p, b.slab, (size_t)cap * SPLAT_F4);
+  take(p, b.ents2, (size_t)cap);
+  take(p, b.point_list, (size_t)cap + 16);
   return b;
 }
 size_t binning_bytes(long long R) {
   BinView b = carve_binning(nullptr, R);
-  return reinterpret_cast<size_t>(b.slab + (size_t)R * SPLAT_F4) + 512;
+  return reinterpret_cast<size_t>(b.point_list + (size_t)R + 16) + 512;
 }
 
 namespace {
@@ -169,7 +170,7 @@ __global__ void k_export_geom(int P, GeomView g, float* means2D, float* conic_op
 }
 __global__ void k_export_list(long long R, BinView b, uint32_t* point_list) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < R) point_list[i] = (uint32_t)__float_as_int(b.slab[(size_t)i * SPLAT_F4 + 2].z);
+  if (i < R) point_list[i] = b.point_list[i];
 }
 __global__ void k_export_image(int N, int T, ImageView im, uint32_t* ranges, uint32_t* n_contrib, float* final_T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,7 +277,7 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
     { Prof pf(3, st); launch_tile_sort(T, g, im, b, st); }
     if (!stage_ok(dbg, st, "tile_sort")) return -1;
   }
-  { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, out_color, out_depth, out_median_depth, out_opacity, st); }
+  { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, g, out_color, out_depth, out_median_depth, out_opacity, st); }
   if (!stage_ok(dbg, st, "render_fwd")) return -1;
   return cap;
 }

@@ -11,8 +11,9 @@
 //            L2 address for a crowded tile;
 //   level 2  each tile's segment is sorted by one CTA (MSD split into depth buckets + one warp-level bitonic
 //            network per bucket) -- in shared memory when it fits, in global memory (L2-resident) otherwise --
-//            and the sorted order is materialised as a contiguous slab of 48-byte splat records, which is what
-//            the render kernels stream with TMA bulk copies.
+//            and the sorted order is written as the list of Gaussian indices (the reference's point_list); the
+//            render kernels gather the 48-byte splat records through it, asynchronously, only as far as the
+//            tile actually gets consumed.
 // Order parity: the reference's sort is stable and its emit order is ascending Gaussian index
 // (rasterizer_impl.cu:98-108), so "stable by (tile, depth bits)" == total order by
 // (tile, depth bits, gaussian index).  Level 2 compares whole 64-bit entries, so the result never depends on
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
   if (n == 0) return;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   u64* seg = b.ents + range.x;
-  float4* out = b.slab + (size_t)range.x * SPLAT_F4;
+  uint32_t* out = b.point_list + range.x;
   const u64* sorted;
 
   if (dbg_mode == 1) {
@@ -188,10 +189,10 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     sorted = sort_smem;
   } else {
     const bool in_smem = n <= SORT_CAP;
-    // A: unsorted input, B: bucketed + sorted output.  Large tiles ping-pong between the entry segment and the
-    // tile's (not yet written) slab region, both L2-resident.
+    // A: unsorted input, B: bucketed + sorted output (shared memory, or the L2-resident scratch segment for a
+    // tile with more instances than fit).
     const u64* A = seg;
-    u64* B = in_smem ? sort_smem : reinterpret_cast<u64*>(out);
+    u64* B = in_smem ? sort_smem : b.ents2 + range.x;
     if (tid < 256) sh.cnt[tid] = 0;
     if (tid == 0) sh.diff = 0;
     __syncthreads();
@@ -239,24 +240,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
       }
     }
     __syncthreads();
-    if (!in_smem) {
-      // the result sits in the slab region that the gather below overwrites: move it to the entry segment
-      for (unsigned i = tid; i < n; i += SORT_THREADS) seg[i] = B[i];
-      __syncthreads();
-      sorted = seg;
-    } else {
-      sorted = B;
-    }
+    sorted = B;
   }
-  // gather the splat records in sorted order into the tile's contiguous slab
-  if (dbg_mode == 2) return;  // timing experiment: no gather
-  // (three consecutive lanes move the three 16-byte pieces of one record: loads of a record share its two
-  // sectors and every warp store is one contiguous 512-byte run of the slab)
-  for (unsigned c = tid; c < 3 * n; c += SORT_THREADS) {
-    const unsigned rec = c / 3, part = c - 3 * rec;
-    const unsigned id = (unsigned)sorted[rec];
-    out[c] = g.splat[(size_t)id * SPLAT_F4 + part];
-  }
+  // the sorted order, as Gaussian indices (what the render kernels walk)
+  if (dbg_mode == 2) return;
+  for (unsigned i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)sorted[i];
 }
 
 }  // namespace

@@ -17,8 +17,8 @@ constexpr int TILE_PIX = TILE_X * TILE_Y;
 constexpr int SUBBINS = 16;
 
 // ---------------------------------------------------------------------------------------------
-// Per-Gaussian projected record ("splat"), 48 B = 3 x float4.  The same record is the element of the
-// per-tile slab that the render kernels stream with cp.async.bulk (TMA) into shared memory.
+// Per-Gaussian projected record ("splat"), 48 B = 3 x float4: what the render kernels stage into shared
+// memory for every sorted tile instance (asynchronous 16-byte copies, gsr_render.cu).
 //   q0 = { mean2D.x, mean2D.y, conic.A, conic.B }
 //   q1 = { conic.C, opacity, view-depth, rgb.r }
 //   q2 = { rgb.g, rgb.b, bits(gaussian index), bits(radius) }
@@ -53,8 +53,9 @@ struct ImageView {
   uint32_t* tile_maxc;    // [T] max n_contrib over the tile's pixels (bounds the backward traversal)
 };
 struct BinView {
-  unsigned long long* ents;  // [cap] (depth bits << 32 | gaussian index), grouped by tile
-  float4* slab;              // [cap][3] sorted, gathered splat records
+  unsigned long long* ents;   // [cap] (depth bits << 32 | gaussian index), grouped by tile (level-1 output)
+  unsigned long long* ents2;  // [cap] scratch of the level-2 sort for tiles that exceed shared memory
+  uint32_t* point_list;       // [cap] Gaussian index per sorted tile instance (== BinningState::point_list)
 };
 
 size_t geom_bytes(int P);
@@ -83,7 +84,7 @@ void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStrea
 void launch_tile_scan(ImageView im, int T, cudaStream_t st);
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
-void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, float* out_color, float* out_depth,
+void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, float* out_color, float* out_depth,
                        float* out_median, float* out_opacity, cudaStream_t st);
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,

@@ -7,9 +7,11 @@
 // and un-normalised depth / no-background colour outputs.
 //
 // What is different (B200):
-//  * the tile's sorted instances are one contiguous slab of 48-byte records (gsr_binning.cu) streamed into
-//    shared memory with cp.async.bulk (TMA) + mbarrier, double buffered -- no per-thread gathers through
-//    point_list, and rgb/depth come from shared memory instead of per-pair global loads (forward.cu:365-366);
+//  * a dedicated producer warp walks the tile's sorted index list and stages the 48-byte splat records of
+//    the next batches into a shared-memory ring with asynchronous 16-byte copies (cp.async, completion on an
+//    mbarrier), NSTAGE batches ahead of the 8 consumer warps -- no CTA-wide barrier in the loop, and
+//    rgb/depth come from shared memory instead of per-pair global loads (forward.cu:365-366).  Only the
+//    part of the list a tile really consumes is ever gathered (early termination / n_contrib bound);
 //  * each warp owns an 8x4 pixel sub-tile and first tests every staged Gaussian against its sub-tile with a
 //    conservative bound on alpha (minimum of the conic form over the rectangle); only survivors are
 //    evaluated.  A pair is skipped only if the reference would `continue` past it for every pixel of the
@@ -47,6 +49,26 @@ __device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(b)
                : "memory");
+}
+// asynchronous 16-byte global->shared copy (LDGSTS, L2 only) and its completion hook on an mbarrier
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+  // the arrival fires once all of this thread's earlier cp.async have landed; .noinc: counted in the init value
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// producer warp: gather `cnt` records listed in ids[0,cnt) into a stage
+__device__ __forceinline__ void stage_gather(float4* dst, const float4* __restrict__ splat,
+                                             const uint32_t* __restrict__ ids, int cnt, int lane,
+                                             unsigned long long* full) {
+  for (int r = lane; r < cnt; r += 32) {
+    const float4* src = splat + (size_t)ids[r] * SPLAT_F4;
+    cp_async16(dst + r * SPLAT_F4 + 0, src + 0);
+    cp_async16(dst + r * SPLAT_F4 + 1, src + 1);
+    cp_async16(dst + r * SPLAT_F4 + 2, src + 2);
+  }
+  cp_async_arrive(full);
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -111,9 +133,9 @@ __device__ __forceinline__ bool may_touch(const float4 q0, const float4 q1, floa
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory ring shared by both kernels: NSTAGE slab batches, `full` barriers completed by the TMA
-// transaction count, `empty` barriers by one arrival per consumer warp.  Warp NCONS (the 9th) is the
-// producer: one elected lane re-arms a stage and issues the bulk copy as soon as every consumer released it.
+// Shared-memory ring shared by both kernels: NSTAGE record batches, `full` barriers completed by the
+// producer lanes' cp.async arrivals, `empty` barriers by one arrival per consumer warp.  Warp NCONS (the 9th)
+// is the producer: it refills a stage as soon as every consumer warp released it.
 // Consumer warps never meet at a CTA-wide barrier inside the loop, so a sub-tile with little work does not
 // wait for a crowded one batch by batch.
 // ---------------------------------------------------------------------------------------------
@@ -128,7 +150,7 @@ struct Ring {
 __device__ __forceinline__ void ring_init(Ring& r) {
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; s++) { mbar_init(&r.full[s], 1); mbar_init(&r.empty[s], NCONS); }
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(&r.full[s], 32); mbar_init(&r.empty[s], NCONS); }
     r.ndone = 0;
     fence_mbar_init();
   }
@@ -139,6 +161,7 @@ __device__ __forceinline__ void ring_init(Ring& r) {
 // forward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
+                                                               const float4* __restrict__ splat,
                                                                float* __restrict__ out_color,
                                                                float* __restrict__ out_depth,
                                                                float* __restrict__ out_median,
@@ -149,31 +172,30 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
   const uint2 range = im.tile_range[tile];
   const int n = (int)(range.y - range.x);
   const int nb = (n + RB - 1) / RB;
-  const float4* slab = bin.slab + (size_t)range.x * SPLAT_F4;
+  const uint32_t* ids = bin.point_list + range.x;
   ring_init(ring);
 
   if (warp == NCONS) {
-    // ---------------- producer ----------------
-    if (lane == 0) {
-      int issued = 0;
-      for (int b = 0; b < nb; b++) {
-        const int s = b % NSTAGE;
+    // ---------------- producer warp ----------------
+    int issued = 0;
+    for (int b = 0; b < nb; b++) {
+      const int s = b % NSTAGE;
+      bool stop = false;
+      if (lane == 0) {
         if (b >= NSTAGE) {
           const unsigned par = (unsigned)((b / NSTAGE - 1) & 1);
-          bool stop = false;
           while (!mbar_try(&ring.empty[s], par)) {
             if (*(volatile unsigned*)&ring.ndone == NCONS) { stop = true; break; }
           }
-          if (stop) break;
         }
-        if (*(volatile unsigned*)&ring.ndone == NCONS) break;
-        const int cnt = min(RB, n - b * RB);
-        tma_load(ring.buf[s], slab + (size_t)b * STAGE_F4, (unsigned)cnt * SPLAT_BYTES, &ring.full[s]);
-        issued = b + 1;
+        if (*(volatile unsigned*)&ring.ndone == NCONS) stop = true;  // every pixel of the tile is finished
       }
-      // every bulk copy must have landed before the CTA's shared memory is released
-      for (int b = max(0, issued - NSTAGE); b < issued; b++) mbar_wait(&ring.full[b % NSTAGE], (unsigned)((b / NSTAGE) & 1));
+      if (__shfl_sync(FULL, (int)stop, 0)) break;
+      stage_gather(ring.buf[s], splat, ids + b * RB, min(RB, n - b * RB), lane, &ring.full[s]);
+      issued = b + 1;
     }
+    // every copy must have landed before the CTA's shared memory is released
+    for (int b = max(0, issued - NSTAGE); b < issued; b++) mbar_wait(&ring.full[b % NSTAGE], (unsigned)((b / NSTAGE) & 1));
     return;
   }
 
@@ -281,7 +303,9 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
 // backward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int gx, const float* __restrict__ bg,
-                                                               ImageView im, BinView bin, float* __restrict__ grad,
+                                                               ImageView im, BinView bin,
+                                                               const float4* __restrict__ splat,
+                                                               float* __restrict__ grad,
                                                                const float* __restrict__ dL_dpix,
                                                                const float* __restrict__ dL_ddepthpix,
                                                                const float* __restrict__ dL_dmedpix,
@@ -293,20 +317,21 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
   const int nmax = (int)min(im.tile_maxc[tile], range.y - range.x);
   if (nmax == 0) return;
   const int nb = (nmax + RB - 1) / RB;
-  const float4* slab = bin.slab + (size_t)range.x * SPLAT_F4;
+  const uint32_t* ids = bin.point_list + range.x;
   ring_init(ring);
 
   // batch b (counted from the back) covers list positions [lo_b, hi_b), hi_b = nmax - b*RB
   if (warp == NCONS) {
-    if (lane == 0) {
-      for (int b = 0; b < nb; b++) {
-        const int s = b % NSTAGE;
-        if (b >= NSTAGE) mbar_wait(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
-        const int hi = nmax - b * RB, lo = max(0, hi - RB);
-        tma_load(ring.buf[s], slab + (size_t)lo * SPLAT_F4, (unsigned)(hi - lo) * SPLAT_BYTES, &ring.full[s]);
+    for (int b = 0; b < nb; b++) {
+      const int s = b % NSTAGE;
+      if (b >= NSTAGE) {
+        if (lane == 0) mbar_wait(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
+        __syncwarp();
       }
-      // the consumers wait on every batch, so all copies have landed when they leave; nothing to drain
+      const int hi = nmax - b * RB, lo = max(0, hi - RB);
+      stage_gather(ring.buf[s], splat, ids + lo, hi - lo, lane, &ring.full[s]);
     }
+    // the consumers wait on every batch, so all copies have landed when they leave; nothing to drain
     return;
   }
 
@@ -432,16 +457,17 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
 
 }  // namespace
 
-void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, float* out_color, float* out_depth,
-                       float* out_median, float* out_opacity, cudaStream_t st) {
-  k_render_fwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, out_color, out_depth, out_median, out_opacity);
+void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, float* out_color,
+                       float* out_depth, float* out_median, float* out_opacity, cudaStream_t st) {
+  k_render_fwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median,
+                                                  out_opacity);
 }
 
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
                        const float* dL_dopacity, cudaStream_t st) {
-  k_render_bwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.grad, dL_dpix, dL_ddepth, dL_dmedian,
-                                                  dL_dopacity);
+  k_render_bwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
+                                                  dL_dmedian, dL_dopacity);
 }
 
 }  // namespace gsr
