@@ -48,46 +48,67 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe) through NVML from a
+    background thread (polling `nvidia-smi -lms` from a child process stalled the CUDA launch path by several ms
+    per step on these hosts; NVML calls every 200 ms do not).  Falls back to nvidia-smi if pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
-    def __init__(self, gpu_index):
-        self.idx, self.p = gpu_index, None
+    def __init__(self, gpu_index, period=0.2):
+        self.idx, self.period = gpu_index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop, self._thr, self._h = None, None, None
+
+    def _phys_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if self.idx < len(ids) and ids[self.idx].strip().isdigit():
+                return int(ids[self.idx])
+        return self.idx
+
+    def _sample(self, nv):
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for name, bit in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def start(self):
+        import threading
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                      text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self._h = nv.nvmlDeviceGetHandleByIndex(self._phys_index())
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self._h = None
+            return
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                self._sample(nv)
+                self._stop.wait(self.period)
+        self._sample(nv)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.p is None:
+        if self._h is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.p.terminate()
+        self._stop.set()
+        self._thr.join(timeout=2)
         try:
-            out, _ = self.p.communicate(timeout=5)
+            import pynvml as nv
+            self._sample(nv)
         except Exception:
-            self.p.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            pass
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
 
 
 class HostCamera:
