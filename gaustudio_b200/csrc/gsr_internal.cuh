@@ -77,6 +77,7 @@ struct FwdArgs {
   // stored pieces f_dc [P,1,3] + f_rest [P,M-1,3]; the kernel applies exp / normalize / sigmoid / cat itself.
   int fused;
   const float *f_dc, *f_rest;
+  int sh_bulk;  // f_dc / f_rest are 16-byte aligned: stage each CTA's contiguous SH block with TMA bulk copies
 };
 
 // ---- launch wrappers (each enqueues on `st`) ----
@@ -102,6 +103,7 @@ struct BwdArgs {
   int fused;
   const float *f_dc, *f_rest, *opacities_raw;
   float *dL_df_dc, *dL_df_rest;
+  int sh_bulk;  // as in FwdArgs; the SH gradient block leaves through a TMA bulk store as well
 };
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st);
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,

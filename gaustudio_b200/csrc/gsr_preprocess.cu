@@ -27,6 +27,37 @@ __device__ const float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 
 struct V3 { float x, y, z; };
 
+// ---- TMA (cp.async.bulk) staging of a CTA's contiguous SH block: 256 Gaussians x (M-1) x 12 B of f_rest and
+// 256 x 12 B of f_dc land in shared memory while the threads do the projection math; rows of 3 / 45 words have
+// odd strides, so per-thread row reads are bank-conflict free.  The backward writes its SH gradients into the
+// same rows and ships the block with one bulk store per tensor.
+constexpr int PRE_THREADS = 256;
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_init_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait0(unsigned long long* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PWAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra PDONE;\n"
+      "bra PWAIT;\n"
+      "PDONE:\n"
+      "}\n" ::"r"(smem_addr(bar)) : "memory");
+}
+
 // column-major 3x3, m[c][r]; product written in the accumulation order of glm's mat3*mat3
 // (third_party/glm/glm/detail/type_mat3x3.inl:486-518) which the reference kernels inherit.
 struct Mat3 { float m[3][3]; };
@@ -157,9 +188,21 @@ __device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, in
 // ---------------------------------------------------------------------------------------------
 // K1: forward.cu:155-256
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
+  extern __shared__ __align__(128) float sh_stage[];  // [256][3] f_dc rows, then [256][(M-1)*3] f_rest rows
+  __shared__ __align__(8) unsigned long long sh_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  // whole CTA inside the array, coefficients beyond DC needed -> TMA staging
+  const bool bulk = a.sh_bulk && a.D > 0 && (blockIdx.x + 1) * PRE_THREADS <= a.P;
+  const int rest_row = (a.M - 1) * 3;
+  if (bulk && threadIdx.x == 0) {
+    const unsigned b_dc = PRE_THREADS * 3 * 4, b_rest = PRE_THREADS * rest_row * 4;
+    bar_init_expect(&sh_bar, b_dc + b_rest);
+    bulk_load(sh_stage, a.f_dc + (size_t)blockIdx.x * PRE_THREADS * 3, b_dc, &sh_bar);
+    bulk_load(sh_stage + PRE_THREADS * 3, a.f_rest + (size_t)blockIdx.x * PRE_THREADS * rest_row, b_rest, &sh_bar);
+  }
+  if (bulk) __syncthreads();  // barrier initialised before anyone polls it
   if (idx < a.P) {
     int radius_i = 0;
     uint32_t tiles = 0;
@@ -217,6 +260,11 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
             // coefficient 0 and coefficients >= 1 may live in two tensors (fused path: f_dc / f_rest)
             const float* sh0 = a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * a.M * 3;
             const float* shr = a.fused ? a.f_rest + (size_t)idx * (a.M - 1) * 3 : sh0 + 3;
+            if (bulk) {
+              bar_wait0(&sh_bar);
+              sh0 = sh_stage + threadIdx.x * 3;
+              shr = sh_stage + PRE_THREADS * 3 + threadIdx.x * rest_row;
+            }
             const float ox = p.x - a.campos[0], oy = p.y - a.campos[1], oz = p.z - a.campos[2];
             const float len = sqrtf(__fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));  // glm::length
             const float x = __fdiv_rn(ox, len), y = __fdiv_rn(oy, len), z = __fdiv_rn(oz, len);
@@ -283,15 +331,30 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(FwdArgs a, GeomView g, I
   for_each_tile(x0, y0, x1, y1, a.gx, [&](int tile, unsigned src) {
     atomicAdd(&im.tile_count[subbin_of(warp_base + (int)src) * T + tile], 1u);
   });
+  if (bulk && threadIdx.x == 0) bar_wait0(&sh_bar);  // the copies must have landed before the CTA retires
 }
 
 // ---------------------------------------------------------------------------------------------
 // K6 + K7 fused: backward.cu:144-274 then 346-412 (K6 assigns dL_dmean, K7 accumulates: quirk 7)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomView g) {
+  extern __shared__ __align__(128) float sh_stage[];  // SH rows in, SH gradient rows out (in place)
+  __shared__ __align__(8) unsigned long long sh_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
   const int M = a.M;
+  const bool bulk = a.sh_bulk && (blockIdx.x + 1) * PRE_THREADS <= a.P;
+  const int rest_row = (M - 1) * 3;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      const unsigned b_dc = PRE_THREADS * 3 * 4, b_rest = PRE_THREADS * rest_row * 4;
+      bar_init_expect(&sh_bar, b_dc + b_rest);
+      bulk_load(sh_stage, a.f_dc + (size_t)blockIdx.x * PRE_THREADS * 3, b_dc, &sh_bar);
+      bulk_load(sh_stage + PRE_THREADS * 3, a.f_rest + (size_t)blockIdx.x * PRE_THREADS * rest_row, b_rest, &sh_bar);
+    }
+    __syncthreads();
+  } else if (idx >= a.P) {
+    return;
+  }
   const bool vis = a.radii[idx] > 0;  // quirk 8
   const float4* ga = reinterpret_cast<const float4*>(g.grad + (size_t)idx * GRAD_F);
   float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
@@ -320,6 +383,11 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
   // SH gradient destinations: one [P,M,3] tensor, or the f_dc / f_rest pair of the fused variant
   float* dsh0 = a.fused ? a.dL_df_dc + (size_t)idx * 3 : (a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr);
   float* dshr = a.fused ? a.dL_df_rest + (size_t)idx * (M - 1) * 3 : (dsh0 ? dsh0 + 3 : nullptr);
+  if (bulk) {  // gradients are written over the staged coefficients and leave with a bulk store
+    bar_wait0(&sh_bar);
+    dsh0 = sh_stage + threadIdx.x * 3;
+    dshr = sh_stage + PRE_THREADS * 3 + threadIdx.x * rest_row;
+  }
   auto dsh_zero = [&](int from) {
     if (!dsh0) return;
     if (from == 0) { dsh0[0] = 0.f; dsh0[1] = 0.f; dsh0[2] = 0.f; from = 1; }
@@ -393,8 +461,8 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
 
     if (have_sh) {
       // SH backward, backward.cu:20-139
-      const float* sh0 = a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * M * 3;
-      const float* shr = a.fused ? a.f_rest + (size_t)idx * (M - 1) * 3 : sh0 + 3;
+      const float* sh0 = bulk ? dsh0 : (a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * M * 3);
+      const float* shr = bulk ? dshr : (a.fused ? a.f_rest + (size_t)idx * (M - 1) * 3 : sh0 + 3);
       const float ox = mean.x - a.campos[0], oy = mean.y - a.campos[1], oz = mean.z - a.campos[2];
       const float len = sqrt(ox * ox + oy * oy + oz * oz);
       const float x = ox / len, y = oy / len, z = oz / len;
@@ -496,6 +564,17 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(BwdArgs a, GeomView g) {
   for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * idx + k] = dcv[k];
   a.dL_dscale[3 * idx] = dsc[0]; a.dL_dscale[3 * idx + 1] = dsc[1]; a.dL_dscale[3 * idx + 2] = dsc[2];
   reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_store(a.dL_df_dc + (size_t)blockIdx.x * PRE_THREADS * 3, sh_stage, PRE_THREADS * 3 * 4);
+      bulk_store(a.dL_df_rest + (size_t)blockIdx.x * PRE_THREADS * rest_row, sh_stage + PRE_THREADS * 3,
+                 PRE_THREADS * rest_row * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released after this
+    }
+  }
 }
 
 // checkFrustum, rasterizer_impl.cu:54-66
@@ -510,10 +589,14 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const f
 }  // namespace
 
 void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st) {
-  k_preprocess_fwd<<<(a.P + 255) / 256, 256, 0, st>>>(a, g, im);
+  const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : 0;
+  if (smem > 48 * 1024 - 64) cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_preprocess_fwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g, im);
 }
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st) {
-  k_preprocess_bwd<<<(a.P + 255) / 256, 256, 0, st>>>(a, g);
+  const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : 0;
+  if (smem > 48 * 1024 - 64) cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_preprocess_bwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g);
 }
 void launch_mark_visible(int P, const float* means3D, const float* view, const float*, unsigned char* present,
                          cudaStream_t st) {

@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
                                                                const float* __restrict__ dL_dpix,
                                                                const float* __restrict__ dL_ddepthpix,
                                                                const float* __restrict__ dL_dmedpix,
-                                                               const float* __restrict__ dL_dopacpix) {
+                                                               const float* __restrict__ dL_dopacpix,
+                                                               const float ddelx_dx, const float ddely_dy) {
   __shared__ __align__(128) Ring ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
@@ -358,7 +359,6 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
   const float bg_term = -T_final * bg_dot;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
   float acc_d = 0.f, last_d = 0.f, acc_o = 0.f, last_o = 0.f, last_alpha = 0.f;
-  const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
   const int warp_max = (int)__reduce_max_sync(FULL, (unsigned)last_contributor);
   // which lane publishes which reduced component (see the butterfly below)
   const bool pub = ((lane & 3) == 0) || lane == 1 || lane == 17;
@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
           const float4 q2 = sb[jj * SPLAT_F4 + 2];
           float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
           if (valid) {
-            const float inv = __frcp_rn(1.f - alpha);  // 1 - alpha >= 0.01
+            float inv;  // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: one MUFU.RCP (gradient tolerance 1e-3)
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
             const float test_T = T * inv;
             const float w = alpha * test_T;
             const float oma = 1.f - last_alpha;
@@ -466,8 +467,10 @@ void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, Ge
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
                        const float* dL_dopacity, cudaStream_t st) {
+  // d(pixel coordinate)/d(ndc): backward.cu:493-494 (double-precision product rounded to float)
+  const float ddelx_dx = (float)(0.5 * W), ddely_dy = (float)(0.5 * H);
   k_render_bwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
-                                                  dL_dmedian, dL_dopacity);
+                                                  dL_dmedian, dL_dopacity, ddelx_dx, ddely_dy);
 }
 
 }  // namespace gsr
