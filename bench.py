@@ -29,7 +29,7 @@ import torch  # noqa: E402
 
 STAGES = ["preprocess_fwd", "tile_scan", "scatter", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd",
           "depth2normal"]
-KERNELS_PER_STEP = 9  # init_header, preprocess_fwd, tile_scan, scatter, tile_sort, render_fwd, render_bwd,
+KERNELS_PER_STEP = 10  # init_header, preprocess_fwd, tile_scan, scatter, tile_sort x2, render_fwd, render_bwd,
 #                        preprocess_bwd, depth2normal (+ the pixel-loss kernels are torch's, not counted)
 
 
@@ -269,10 +269,6 @@ def main():
         hc.upload(dev)  # cameras resident in HBM before the timed region
     sync_all()
     L = _lib.lib()
-    if a.impl == "new":
-        L.gsr_profile_enable(1)
-        ms0 = (ctypes.c_float * 8)(); cn0 = (ctypes.c_int * 8)()
-        L.gsr_profile_read(ms0, cn0)  # drop warm-up records
     sampler = ClockSampler(local_rank)
     sampler.start()
     losses = torch.zeros(K, device=dev)
@@ -286,8 +282,18 @@ def main():
     sync_all()
     ms_dev = parallel.barrier_max_ms(e0.elapsed_time(e1), dev) if a.impl == "new" else e0.elapsed_time(e1)
     clocks = sampler.stop()
+    if a.impl == "new":
+        _C.check_pipeline(wait=True)
+
+    # ---------------- leg 1b: per-kernel CUDA-event times over the same K steps (library-side events around every
+    # launch on the caller's stream).  Kept out of leg 1: NVML polling + per-launch event creation together
+    # stalled the launch path on these hosts (value dropped 4x), each alone did not. ----------------
     stage_ms = None
     if a.impl == "new":
+        L.gsr_profile_enable(1)
+        for i in range(K):
+            step(hcams[Wn + i])
+        sync_all()
         ms = (ctypes.c_float * 8)(); cn = (ctypes.c_int * 8)()
         L.gsr_profile_read(ms, cn)
         L.gsr_profile_enable(0)
@@ -384,7 +390,7 @@ def main():
         "e2e": {"value": (world if a.impl == "new" else 1) * K / (ms_e2e * 1e-3), "unit": "views/s",
                 "h2d_bytes_per_step": hcams[0].nbytes if a.impl == "new" else 0,
                 "d2h_bytes_per_step": 4 if a.impl == "new" else 0, "ms_per_step": ms_e2e / K},
-        "gpu_launches": KERNELS_PER_STEP * K * 2 if a.impl == "new" else 0,
+        "gpu_launches": KERNELS_PER_STEP * K * 3 if a.impl == "new" else 0,  # three timed legs
     }
     if a.impl == "new":
         out["roofline"] = roof

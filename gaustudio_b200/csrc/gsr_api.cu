@@ -84,12 +84,13 @@ ImageView carve_image(char* base, int W, int H) {
   take(p, im.tile_range, T);
   take(p, im.tile_cursor, T * SUBBINS);
   take(p, im.tile_maxc, T);
+  take(p, im.big_tiles, T);
   return im;
 }
 size_t image_bytes(int W, int H) {
   ImageView im = carve_image(nullptr, W, H);
   const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
-  return reinterpret_cast<size_t>(im.tile_maxc + T) + 512;
+  return reinterpret_cast<size_t>(im.big_tiles + T) + 512;
 }
 BinView carve_binning(char* base, long long cap) {
   BinView b;
@@ -111,6 +112,7 @@ __global__ void k_init_header(ImageHeader* h, unsigned long long cap) {
   h->num_rendered = 0;
   h->capacity = cap;
   h->overflow = 0;
+  h->num_big = 0;
 }
 
 // gaustudio/datasets/__init__.py:106-112,307-380 -- same arithmetic order as the torch ops of the reference:

@@ -20,6 +20,7 @@
 // the (non-deterministic) arrival order of the level-1 scatter.
 #include "gsr_internal.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace gsr {
@@ -32,6 +33,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // Tiles are taken in rounds of SCAN_THREADS consecutive tiles (coalesced, 16 independent loads per thread),
 // each round is block-scanned and chained through a running carry.
 constexpr int SCAN_THREADS = 1024;
+constexpr int SORT_CAP_SMALL_ = 4096;  // == SORT_CAP_SMALL below
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T) {
   __shared__ unsigned warp_sums[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -58,9 +60,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T)
       // tiles whose segment does not fit the binning capacity render nothing (pipelined-mode overflow)
       const bool fits = run + c <= cap;
       im.tile_range[t] = (c && fits) ? make_uint2((unsigned)run, (unsigned)(run + c)) : make_uint2(0u, 0u);
+      if (fits && c > (unsigned)SORT_CAP_SMALL_) im.big_tiles[atomicAdd(&im.hdr->num_big, 1u)] = (unsigned)t;
 #pragma unroll
       for (int s = 0; s < SUBBINS; s++) {
-        im.tile_cursor[s * T + t] = fits ? (unsigned)run : 0xffffffffu;
+        im.tile_cursor[s * T + t] = fits ? (unsigned)run : 0x80000000u;  // dropped: slots fail the range test
         run += cnt[s];
       }
     }
@@ -85,15 +88,29 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
   const int w = x1 - x0, n = w * (y1 - y0);
   const unsigned lane = threadIdx.x & 31;
   constexpr int kBig = 32;
+  // cursors of tiles that were dropped for capacity start at DROPPED, so their slots fail the range test
+  const unsigned long long cap = im.hdr->capacity;
+  const unsigned limit = cap < 0x80000000ull ? (unsigned)cap : 0x80000000u;
   auto put = [&](int tile, unsigned dbits, int gidx) {
-    unsigned* cur = &im.tile_cursor[subbin_of(gidx) * T + tile];
-    if (*cur == 0xffffffffu) return;  // tile dropped (capacity overflow)
-    const unsigned slot = atomicAdd(cur, 1u);
-    b.ents[slot] = ((unsigned long long)dbits << 32) | (unsigned)gidx;
+    const unsigned slot = atomicAdd(&im.tile_cursor[subbin_of(gidx) * T + tile], 1u);
+    if (slot < limit) b.ents[slot] = ((unsigned long long)dbits << 32) | (unsigned)gidx;
   };
   if (n > 0 && n <= kBig) {
-    for (int y = y0; y < y1; y++)
-      for (int x = x0; x < x1; x++) put(y * gx + x, depth_bits, idx);
+    // four tiles at a time: the four returning atomics are independent and overlap their L2 round trips
+    const unsigned long long key = ((unsigned long long)depth_bits << 32) | (unsigned)idx;
+    unsigned* cur = im.tile_cursor + subbin_of(idx) * T;
+    for (int base = 0; base < n; base += 4) {
+      unsigned slot[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = base + k;
+        slot[k] = 0xffffffffu;
+        if (i < n) slot[k] = atomicAdd(cur + (y0 + i / w) * gx + x0 + i % w, 1u);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (slot[k] < limit) b.ents[slot[k]] = key;
+    }
   }
   // a splat covering many tiles is walked by the whole warp (see for_each_tile in gsr_preprocess.cu)
   unsigned big = __ballot_sync(FULL, n > kBig);
@@ -109,15 +126,18 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
 }
 
 // ---- level 2: per-tile sort + slab gather ---------------------------------------------------------
-// One CTA per tile.  An MSD split on the 8 highest *varying* bits of the depth key partitions the tile's
-// entries into up to 256 depth buckets (shared-memory atomics: the split need not be stable), then every
-// bucket -- a few dozen entries -- is sorted by one warp with a shuffle bitonic network on the full 64-bit
+// One CTA per tile.  An MSD split maps the depth keys linearly from the tile's own [min, max] onto NB depth
+// buckets (shared-memory atomics: the split need not be stable), then every bucket -- about 8 entries -- is
+// sorted by one warp with a shuffle bitonic network on the full 64-bit
 // entry (depth bits << 32 | gaussian index).  Comparing the whole entry yields the reference's order
 // (stable by depth == ties in ascending Gaussian index) with no dependence on the scatter's arrival order.
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_CAP = 8192;  // entries sorted in shared memory (64 KB); larger tiles use global
-constexpr size_t SORT_SMEM = SORT_CAP * sizeof(unsigned long long);
+// Two launches cover every tile: a small-footprint kernel (4 CTAs/SM) for tiles up to SORT_CAP_SMALL entries and
+// a one-CTA-per-SM kernel with almost all of the SM's shared memory for the crowded ones; only tiles beyond
+// SORT_CAP_BIG entries fall back to sorting in global memory (L2-resident scratch).
+constexpr int SORT_CAP_SMALL = 4096;   // 32 KB
+constexpr int SORT_CAP_BIG = 26624;    // 208 KB (+ 16 KB of bucket counters)
 typedef unsigned long long u64;
 
 // ascending bitonic sort of one key per lane (unused lanes hold ~0ull)
@@ -159,20 +179,28 @@ __device__ __forceinline__ void warp_sort_mem(u64* k, unsigned m, unsigned lane)
   }
 }
 
-struct SortShared {
-  unsigned cnt[256];
-  unsigned start[257];
-  unsigned wsum[8];
-  unsigned diff;
+template <int NB> struct SortShared {
+  unsigned cnt[NB];        // bucket sizes, then running cursors of the split
+  unsigned start[NB + 1];  // exclusive prefix of the bucket sizes
+  unsigned wsum[SORT_WARPS];
+  unsigned dmin, dmax;
 };
 
+// CAP: entries held in shared memory; MIN_N: tiles up to MIN_N entries belong to the other launch;
+// NB: depth buckets of the MSD split (about 8 entries per bucket at CAP).
+template <int CAP, int MIN_N, int NB>
 __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b, int dbg_mode) {
   extern __shared__ __align__(16) u64 sort_smem[];
-  __shared__ SortShared sh;
-  const uint2 range = im.tile_range[blockIdx.x];
-  const unsigned n = range.y - range.x;
-  if (n == 0) return;
+  __shared__ SortShared<NB> sh;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // small launch: one CTA per tile.  big launch: a few CTAs walk the compact list of crowded tiles.
+  const unsigned num_work = MIN_N == 0 ? gridDim.x : im.hdr->num_big;
+  for (unsigned work = blockIdx.x; work < num_work; work += gridDim.x) {
+  const unsigned tile = MIN_N == 0 ? work : im.big_tiles[work];
+  const uint2 range = im.tile_range[tile];
+  const unsigned n = range.y - range.x;
+  if (n <= (unsigned)MIN_N || (MIN_N == 0 && n > (unsigned)CAP)) continue;  // the other launch owns this tile
+  __syncthreads();  // shared memory of the previous tile is free
   u64* seg = b.ents + range.x;
   uint32_t* out = b.point_list + range.x;
   const u64* sorted;
@@ -188,48 +216,62 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     __syncthreads();
     sorted = sort_smem;
   } else {
-    const bool in_smem = n <= SORT_CAP;
+    const bool in_smem = n <= (unsigned)CAP;
     // A: unsorted input, B: bucketed + sorted output (shared memory, or the L2-resident scratch segment for a
     // tile with more instances than fit).
     const u64* A = seg;
     u64* B = in_smem ? sort_smem : b.ents2 + range.x;
-    if (tid < 256) sh.cnt[tid] = 0;
-    if (tid == 0) sh.diff = 0;
+    for (unsigned i = tid; i < NB; i += SORT_THREADS) sh.cnt[i] = 0;
+    if (tid == 0) { sh.dmin = 0xffffffffu; sh.dmax = 0u; }
     __syncthreads();
-    // digit = the 8 highest depth bits that are not identical across the tile
-    const unsigned first = (unsigned)(A[0] >> 32);
-    unsigned diff = 0;
-    for (unsigned i = tid; i < n; i += SORT_THREADS) diff |= (unsigned)(A[i] >> 32) ^ first;
-    diff = __reduce_or_sync(FULL, diff);
-    if (lane == 0 && diff) atomicOr(&sh.diff, diff);
+    // bucket = linear map of the depth bits from the tile's own [min, max] onto [0, NB): monotone in depth, and
+    // balanced even when the tile's depths span several binades but crowd into one of them
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (unsigned i = tid; i < n; i += SORT_THREADS) { const unsigned d = (unsigned)(A[i] >> 32); lo = min(lo, d); hi = max(hi, d); }
+    lo = __reduce_min_sync(FULL, lo); hi = __reduce_max_sync(FULL, hi);
+    if (lane == 0) { atomicMin(&sh.dmin, lo); atomicMax(&sh.dmax, hi); }
     __syncthreads();
-    diff = sh.diff;
-    const unsigned shift = 32u + (diff ? (unsigned)max(0, 31 - __clz((int)diff) - 7) : 0u);
-    for (unsigned i = tid; i < n; i += SORT_THREADS) atomicAdd(&sh.cnt[(unsigned)(A[i] >> shift) & 255u], 1u);
+    const unsigned dmin = sh.dmin, span = sh.dmax - dmin;
+    // bucket = floor((d - dmin) * NB / (span + 1)) via a 32-bit fixed-point reciprocal (span >= NB here), or the
+    // identity when the tile's keys span fewer values than there are buckets
+    // a bucket costs one 15-step warp network however few entries it holds, so aim at ~20 entries per bucket
+    const unsigned nb = min((unsigned)NB, max(8u, n / 20u));
+    const bool direct = span < nb;
+    const unsigned mult = direct ? 0u : (unsigned)(((u64)nb << 32) / ((u64)span + 1ull));
+    auto bucket = [=](u64 key) {
+      const unsigned d = (unsigned)(key >> 32) - dmin;
+      return direct ? d : __umulhi(d, mult);
+    };
+    for (unsigned i = tid; i < n; i += SORT_THREADS) atomicAdd(&sh.cnt[bucket(A[i])], 1u);
     __syncthreads();
-    if (tid < 256) {  // exclusive scan of the 256 bucket sizes
-      const unsigned c = sh.cnt[tid];
-      unsigned v = c;
+    {  // exclusive scan of the NB bucket sizes: NB / SORT_THREADS consecutive buckets per thread
+      constexpr int PER = (NB + SORT_THREADS - 1) / SORT_THREADS;
+      unsigned c[PER], local = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++) { const unsigned i = tid * PER + k; c[k] = i < NB ? sh.cnt[i] : 0u; local += c[k]; }
+      unsigned v = local;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
       if (lane == 31) sh.wsum[warp] = v;
-      __syncwarp();
-      // the 8 participating warps synchronise through a named barrier (the other 8 skip this block)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      unsigned basew = 0;
+      __syncthreads();
+      unsigned run = v - local;
 #pragma unroll
-      for (int w = 0; w < 8; w++) basew += (w < (int)warp) ? sh.wsum[w] : 0u;
-      sh.start[tid] = basew + v - c;
-      sh.cnt[tid] = basew + v - c;  // running cursor for the split
-      if (tid == 255) sh.start[256] = basew + v;
+      for (int w = 0; w < SORT_WARPS; w++) run += (w < (int)warp) ? sh.wsum[w] : 0u;
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        const unsigned i = tid * PER + k;
+        if (i < NB) { sh.start[i] = run; sh.cnt[i] = run; }
+        run += c[k];
+      }
+      if (tid == SORT_THREADS - 1) sh.start[NB] = run;
     }
     __syncthreads();
     for (unsigned i = tid; i < n; i += SORT_THREADS) {
       const u64 key = A[i];
-      B[atomicAdd(&sh.cnt[(unsigned)(key >> shift) & 255u], 1u)] = key;
+      B[atomicAdd(&sh.cnt[bucket(key)], 1u)] = key;
     }
     __syncthreads();
-    for (unsigned bk = warp; bk < 256; bk += SORT_WARPS) {
+    for (unsigned bk = warp; bk < nb; bk += SORT_WARPS) {
       const unsigned s0 = sh.start[bk], m = sh.start[bk + 1] - s0;
       if (m <= 1) continue;
       if (m <= 32) {
@@ -243,8 +285,9 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     sorted = B;
   }
   // the sorted order, as Gaussian indices (what the render kernels walk)
-  if (dbg_mode == 2) return;
+  if (dbg_mode == 2) continue;
   for (unsigned i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)sorted[i];
+  }
 }
 
 }  // namespace
@@ -256,9 +299,13 @@ void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, c
 }
 
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
-  cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM);  // per device
   static const int dbg_mode = getenv("GSR_SORT_DEBUG") ? atoi(getenv("GSR_SORT_DEBUG")) : 0;  // timing experiments only
-  k_tile_sort<<<T, SORT_THREADS, SORT_SMEM, st>>>(g, im, b, dbg_mode);
+  auto small = k_tile_sort<SORT_CAP_SMALL, 0, 512>;
+  auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_SMALL, 2048>;
+  constexpr int smem_small = SORT_CAP_SMALL * 8, smem_big = SORT_CAP_BIG * 8;
+  cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);  // per device
+  small<<<T, SORT_THREADS, smem_small, st>>>(g, im, b, dbg_mode);
+  big<<<148, SORT_THREADS, smem_big, st>>>(g, im, b, dbg_mode);  // one CTA per SM, loops over hdr->num_big tiles
 }
 
 }  // namespace gsr

@@ -31,7 +31,8 @@ struct ImageHeader {            // first 256 B of the image buffer
   unsigned long long num_rendered;  // R = sum of tile counts (written by the scan kernel)
   unsigned long long capacity;      // binning capacity the scatter / sort / render kernels may use
   unsigned int overflow;            // set when num_rendered > capacity (pipelined mode)
-  unsigned int pad[11];
+  unsigned int num_big;             // tiles with more instances than the small sort kernel holds
+  unsigned int pad[10];
 };
 
 struct GeomView {      // carved from the geometry buffer, all 256-B aligned
@@ -51,6 +52,7 @@ struct ImageView {
   uint2* tile_range;      // [T] [start,end) into the sorted instance list; (0,0) when empty
   uint32_t* tile_cursor;  // [SUBBINS][T] write cursors of the scatter pass
   uint32_t* tile_maxc;    // [T] max n_contrib over the tile's pixels (bounds the backward traversal)
+  uint32_t* big_tiles;    // [T] compact list of crowded tiles (hdr->num_big entries), built by the scan
 };
 struct BinView {
   unsigned long long* ents;   // [cap] (depth bits << 32 | gaussian index), grouped by tile (level-1 output)
