@@ -314,6 +314,9 @@ def main():
     if a.impl == "new":
         _C.check_pipeline(wait=True)
 
+    if world > 1 and torch.distributed.is_initialized() and rank != 0:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
 
@@ -406,7 +409,10 @@ def main():
         out["cpu_baseline"] = {"value": out["e2e"]["value"], "unit": "views/s", "cores": 1, "kind": "reference",
                                "sample": "the reference has no CPU implementation of this path: its own CUDA "
                                          "extension (unmodified sources, sm_100a) driven by one host thread"}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    if world > 1 and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return 0
 
 
