@@ -274,8 +274,10 @@ def main():
     losses = torch.zeros(K, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(K):
         losses[i] = step(hcams[Wn + i])
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K  # host time to enqueue a step (no sync inside)
     if a.impl == "new":
         all_losses = parallel.gather_view_losses(losses, K * world, rank, world)  # the one collective
     e1.record()
@@ -301,15 +303,24 @@ def main():
         _C.check_pipeline(wait=True)
 
     # ---------------- leg 2: end to end through the public API with host buffers ("e2e") ----------------
-    host_loss = torch.empty(1).pin_memory()
+    host_loss = torch.zeros(K).pin_memory()      # pinned ring: one slot per step
+    done = [torch.cuda.Event() for _ in range(K)]
+    read_back = []
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(K):
-        hc = hcams[Wn + i].upload(dev)               # H2D of this step's inputs from pinned memory
-        host_loss.copy_(step(hc).reshape(1))         # D2H read of the step's result
+        hc = hcams[Wn + i].upload(dev)                              # H2D of this step's inputs from pinned memory
+        host_loss[i:i + 1].copy_(step(hc).reshape(1), non_blocking=True)   # D2H of the step's result ...
+        done[i].record()
+        if i > 0:                                                   # ... consumed one step later, like a trainer
+            done[i - 1].synchronize()                               # logging its loss: the GPU never waits for the host
+            read_back.append(float(host_loss[i - 1]))
+    done[K - 1].synchronize()
+    read_back.append(float(host_loss[K - 1]))
     e3.record()
     sync_all()
+    assert len(read_back) == K and all(math.isfinite(v) for v in read_back)
     ms_e2e = parallel.barrier_max_ms(e2.elapsed_time(e3), dev) if a.impl == "new" else e2.elapsed_time(e3)
     if a.impl == "new":
         _C.check_pipeline(wait=True)
@@ -390,9 +401,12 @@ def main():
                    "forward_mode": "pipelined (no host sync; overflow-checked)" if a.pipelined and a.impl == "new" else
                                    "exact (one blocking 8-byte D2H per view, like the reference)"},
         "clocks": clocks,
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),  # if this is >= ms_per_step the run is host-bound
         "e2e": {"value": (world if a.impl == "new" else 1) * K / (ms_e2e * 1e-3), "unit": "views/s",
                 "h2d_bytes_per_step": hcams[0].nbytes if a.impl == "new" else 0,
-                "d2h_bytes_per_step": 4 if a.impl == "new" else 0, "ms_per_step": ms_e2e / K},
+                "d2h_bytes_per_step": 4 if a.impl == "new" else 0, "ms_per_step": ms_e2e / K,
+                "note": "every step: camera H2D from pinned memory + loss D2H into a pinned ring, read on the host one "
+                        "step later (the host blocks on step k-1 while step k runs)"},
         "gpu_launches": KERNELS_PER_STEP * K * 3 if a.impl == "new" else 0,  # three timed legs
     }
     if a.impl == "new":
