@@ -18,7 +18,7 @@ from . import _lib
 _pipeline = threading.local()
 
 
-def set_pipelined(enabled, slack=1.5):
+def set_pipelined(enabled, slack=1.25):
     _pipeline.enabled = bool(enabled)
     _pipeline.slack = float(slack)
     _pipeline.hw = {}
@@ -33,6 +33,13 @@ def _pl():
     return _pipeline
 
 
+def _quantise(r, slack):
+    """Binning capacity for a view that needed r instances: slack on top, rounded up to 1 Mi entries so the
+    buffer size (and with it the caching allocator's block) stops changing after the first few views."""
+    q = 1 << 20
+    return ((int(r * slack) + 4096 + q - 1) // q) * q
+
+
 def check_pipeline(wait=False):
     """Raise if a pipelined forward overflowed its binning capacity.  wait=True drains all pending views."""
     pl = _pl()
@@ -42,7 +49,7 @@ def check_pipeline(wait=False):
             ev.synchronize()
         if ev.query():
             r = int(host.item())
-            pl.hw[key] = max(pl.hw.get(key, 0), int(r * pl.slack) + 4096)
+            pl.hw[key] = max(pl.hw.get(key, 0), _quantise(r, pl.slack))
             if r > cap:
                 pl.pending = []
                 raise RuntimeError(f"gsr: pipelined forward overflowed its binning capacity ({r} > {cap}); "
@@ -166,7 +173,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 ev.record(stream)
                 pl.pending.append((host, ev, cap, key))
             else:  # first view of this shape ran in exact mode: seed the high-water mark
-                pl.hw[key] = int(r * pl.slack) + 4096
+                pl.hw[key] = _quantise(r, pl.slack)
     return int(r), out_color, out_depth, out_median, out_opacity, radii, geom.buf, binning.buf, img.buf
 
 
