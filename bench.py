@@ -323,6 +323,7 @@ def main():
     host_loss = torch.zeros(K).pin_memory()      # pinned ring: one slot per step
     done = [torch.cuda.Event() for _ in range(K)]
     read_back = []
+    lag = max(1, nstreams)  # the host stays this many steps ahead of the results it reads back
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -334,11 +335,12 @@ def main():
             hc = hcams[Wn + i].upload(dev)                          # H2D of this step's inputs from pinned memory
             host_loss[i:i + 1].copy_(step(hc).reshape(1), non_blocking=True)   # D2H of the step's result ...
             done[i].record()
-        if i > 0:                                                   # ... consumed one step later, like a trainer
-            done[i - 1].synchronize()                               # logging its loss: the GPU never waits for the host
-            read_back.append(float(host_loss[i - 1]))
-    done[K - 1].synchronize()
-    read_back.append(float(host_loss[K - 1]))
+        if i >= lag:                                                # ... consumed `lag` steps later, like a trainer
+            done[i - lag].synchronize()                             # logging its loss: the GPU never waits for the host
+            read_back.append(float(host_loss[i - lag]))
+    for j in range(max(0, K - lag), K):
+        done[j].synchronize()
+        read_back.append(float(host_loss[j]))
     if nstreams > 1:
         for st in streams:
             main_stream.wait_stream(st)
@@ -430,8 +432,8 @@ def main():
         "e2e": {"value": (world if a.impl == "new" else 1) * K / (ms_e2e * 1e-3), "unit": "views/s",
                 "h2d_bytes_per_step": hcams[0].nbytes if a.impl == "new" else 0,
                 "d2h_bytes_per_step": 4 if a.impl == "new" else 0, "ms_per_step": ms_e2e / K,
-                "note": "every step: camera H2D from pinned memory + loss D2H into a pinned ring, read on the host one "
-                        "step later (the host blocks on step k-1 while step k runs)"},
+                "note": "every step: camera H2D from pinned memory + loss D2H into a pinned ring, read on the host "
+                        "`streams_per_gpu` steps later (the host blocks on step k-lag while steps k-lag+1..k run)"},
         "gpu_launches": KERNELS_PER_STEP * K * 3 if a.impl == "new" else 0,  # three timed legs
     }
     if a.impl == "new":
