@@ -74,24 +74,17 @@ class VanillaRenderer(BaseRenderer):
     def render(self, viewpoint_camera, gaussian_model):
         if not self._can_fuse(gaussian_model):
             return super().render(viewpoint_camera, gaussian_model)
-        import math
-        from ..rasterizer import GaussianRasterizationSettings, rasterize_gaussians_fused
+        from ..rasterizer import rasterize_gaussians_fused
+        from .base import pack_result, settings_for
         m = gaussian_model
-        xyz = m._xyz
-        screenspace_points = torch.zeros_like(xyz, requires_grad=True)
-        rs = GaussianRasterizationSettings(
-            int(viewpoint_camera.image_height), int(viewpoint_camera.image_width),
-            math.tan(viewpoint_camera.FoVx * 0.5), math.tan(viewpoint_camera.FoVy * 0.5), self.bg_color,
-            self.scaling_modifier, viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform,
-            m.active_sh_degree, viewpoint_camera.camera_center, False, self.debug)
-        P = xyz.shape[0]
+        P = m._xyz.shape[0]
+        screenspace = torch.zeros_like(m._xyz, requires_grad=True)
+        rs = settings_for(viewpoint_camera, bg=self.bg_color, scale_modifier=self.scaling_modifier,
+                          sh_degree=m.active_sh_degree, debug=self.debug)
         image, radii, depth, median_map, opacity = rasterize_gaussians_fused(
-            xyz, screenspace_points, m._f_dc.reshape(P, -1, 3), m._f_rest.reshape(P, -1, 3), m._opacity, m._scale,
-            m._rot, rs)
-        return {"render": image, "rendered_depth": depth, "rendered_median_depth": median_map[0:1],
-                "rendered_median_weight": median_map[1:2], "rendered_median_id": median_map[2:3].int(),
-                "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
-                "rendered_final_opacity": opacity, "radii": radii}
+            m._xyz, screenspace, m._f_dc.reshape(P, -1, 3), m._f_rest.reshape(P, -1, 3), m._opacity, m._scale, m._rot,
+            rs)
+        return pack_result(image, radii, depth, median_map, opacity, screenspace)
 
     def get_gaussians_properties(self, viewpoint_camera, gaussian_model):
         xyz = gaussian_model.get_attribute("xyz")

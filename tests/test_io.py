@@ -1,0 +1,68 @@
+"""PLY / cameras.json I/O: layout of the reference's export, loader semantics of its load."""
+import json
+import math
+
+import numpy as np
+import torch
+
+from gaustudio_b200 import io
+from gaustudio_b200.camera import look_at_camera
+from gaustudio_b200.synthetic import make_scene
+
+
+def test_ply_roundtrip_and_layout(tmp_path):
+    m = make_scene(257, 1.0, 0.05, seed=9)
+    p = tmp_path / "pc.ply"
+    io.export_ply(m, str(p))
+    raw = p.read_bytes()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode().splitlines()
+    assert lines[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 257"]
+    props = [l.split()[2] for l in lines if l.startswith("property")]
+    # vanilla_sg.py:159-181 (construct_list_of_attributes)
+    assert props == (["x", "y", "z", "nx", "ny", "nz"] + [f"f_dc_{i}" for i in range(3)] +
+                     [f"f_rest_{i}" for i in range(45)] + ["opacity"] + [f"scale_{i}" for i in range(3)] +
+                     [f"rot_{i}" for i in range(4)])
+    assert all(l.split()[1] == "float" for l in lines if l.startswith("property"))
+    assert len(body) == 257 * len(props) * 4
+    row0 = np.frombuffer(body[:len(props) * 4], "<f4")
+    assert np.allclose(row0[:3], m._xyz[0].numpy()) and np.all(row0[3:6] == 0)
+    # SH is written channel-major: f_rest_k = coefficient (k % 15)+1 of channel k // 15 (vanilla_sg.py:147-148)
+    assert row0[6 + 3 + 16] == m._f_rest[0, 1, 1]
+    back = io.load_ply(str(p))
+    assert back.active_sh_degree == 0 and back.max_sh_degree == 3 and back.num_points == 257
+    for name in ("_xyz", "_scale", "_rot", "_opacity"):
+        assert torch.equal(getattr(back, name), getattr(m, name).reshape(getattr(back, name).shape))
+    assert back._f_dc.shape == (257, 3) and back._f_rest.shape == (257, 45)
+    # the loader keeps the file's flat order (base.py:94-104); get_features reshapes it as (P,-1,3) (vanilla_sg.py:102-106)
+    assert torch.equal(back._f_rest, m._f_rest.transpose(1, 2).flatten(start_dim=1))
+    assert back.get_features.shape == (257, 16, 3)
+    assert torch.equal(back.get_features[:, 0], m._f_dc[:, 0])  # DC is layout-invariant ([P,1,3])
+
+
+def test_ascii_ply_and_extra_elements(tmp_path):
+    p = tmp_path / "a.ply"
+    p.write_text("ply\nformat ascii 1.0\ncomment hi\nelement vertex 2\nproperty float x\nproperty float y\n"
+                 "property float z\nproperty float opacity\nproperty float scale_1\nproperty float scale_0\n"
+                 "property float scale_2\nproperty float rot_0\nproperty float rot_1\nproperty float rot_2\n"
+                 "property float rot_3\nproperty float f_dc_0\nproperty float f_dc_1\nproperty float f_dc_2\n"
+                 "element face 0\nproperty list uchar int vertex_indices\nend_header\n"
+                 "1 2 3 0.5 11 10 12 1 0 0 0 .1 .2 .3\n4 5 6 -0.5 21 20 22 0 1 0 0 .4 .5 .6\n")
+    m = io.load_ply(str(p))
+    assert m._xyz.tolist() == [[1, 2, 3], [4, 5, 6]]
+    assert m._scale.tolist() == [[10, 11, 12], [20, 21, 22]]  # ordered by numeric suffix, not file order
+    assert m._f_rest.shape == (2, 45) and float(m._f_rest.abs().max()) == 0
+
+
+def test_cameras_json_matches_look_at(tmp_path):
+    cam = look_at_camera((2.0, 1.0, 0.5), (0, 0, 0), 320, 240, math.radians(60), math.radians(47))
+    c2w = np.linalg.inv(cam.world_view_transform.numpy().T.astype(np.float64))
+    fx = 320 / (2 * math.tan(cam.FoVx / 2)); fy = 240 / (2 * math.tan(cam.FoVy / 2))
+    entry = dict(id=0, img_name="v0", width=320, height=240, position=c2w[:3, 3].tolist(),
+                 rotation=c2w[:3, :3].tolist(), fx=fx, fy=fy)
+    p = tmp_path / "cameras.json"
+    p.write_text(json.dumps([entry]))
+    (back,) = io.load_cameras_json(str(p))
+    assert np.allclose(back.world_view_transform.numpy(), cam.world_view_transform.numpy(), atol=1e-5)
+    assert np.allclose(back.full_proj_transform.numpy(), cam.full_proj_transform.numpy(), atol=1e-5)
+    assert abs(back.FoVx - cam.FoVx) < 1e-9 and (back.image_width, back.image_height) == (320, 240)
