@@ -28,6 +28,7 @@ SIGNATURES = {
                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "gsr_mark_visible": (_I, [_I, _P, _P, _P, _P, _P]),
     "gsr_depth2normal": (_I, [_P, _I, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
+    "gsr_depth2point": (_I, [_P, _I, _I, _F, _F, _F, _F, _P, _P, _P]),
     "gsr_profile_enable": (_I, [_I]),
     "gsr_profile_read": (_I, [_P, _P]),
     "gsr_debug_export": (_I, [_I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

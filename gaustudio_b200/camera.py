@@ -103,6 +103,13 @@ class Camera:
                              [0, fy, self.image_height * self.principal_point_ndc[1]],
                              [0, 0, 1]]).float()
 
+    def depth2point(self, depth, coordinate="camera"):
+        """[H,W] depth -> [H,W,3] points (CUDA restatement of datasets/__init__.py:307-339)."""
+        from . import ops
+        K = self.intrinsics
+        c2w = torch.inverse(self.extrinsics) if coordinate == "world" else None
+        return ops.depth2point(depth, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), c2w)
+
     def depth2normal(self, depth, d_min=1e-3, d_max=100000.0, coordinate="camera"):
         """[H,W] depth -> [H,W,3] normals; CUDA restatement of datasets/__init__.py:342-380 (k=3)."""
         from . import ops

@@ -155,6 +155,29 @@ __global__ void k_depth2normal(const float* __restrict__ depth, int W, int H, fl
   o[0] = n0; o[1] = n1; o[2] = n2;
 }
 
+// Camera.depth2point (gaustudio/datasets/__init__.py:106-112,307-339): back-projection of a depth map to camera
+// or world coordinates (what extract_mesh.py:95-115 feeds the TSDF fusion with).  c2w: row-major 4x4
+// inverse(extrinsics) or NULL.
+__global__ void k_depth2point(const float* __restrict__ depth, int W, int H, float ifx, float ify, float ox, float oy,
+                              const float* __restrict__ c2w, float* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+  if (u >= W || v >= H) return;
+  const float z = depth[(size_t)v * W + u];
+  const float uz = __fmul_rn(__fmul_rn(__fdiv_rn((float)u, (float)(W - 1)), (float)(W - 1)), z);
+  const float vz = __fmul_rn(__fmul_rn(__fdiv_rn((float)v, (float)(H - 1)), (float)(H - 1)), z);
+  float x = __fadd_rn(__fmul_rn(uz, ifx), __fmul_rn(z, ox));
+  float y = __fadd_rn(__fmul_rn(vz, ify), __fmul_rn(z, oy));
+  float zz = z;
+  if (c2w) {
+    const float wx = c2w[0] * x + c2w[1] * y + c2w[2] * z + c2w[3];
+    const float wy = c2w[4] * x + c2w[5] * y + c2w[6] * z + c2w[7];
+    const float wz = c2w[8] * x + c2w[9] * y + c2w[10] * z + c2w[11];
+    x = wx; y = wy; zz = wz;
+  }
+  float* o = out + ((size_t)v * W + u) * 3;
+  o[0] = x; o[1] = y; o[2] = zz;
+}
+
 __global__ void k_export_geom(int P, GeomView g, float* means2D, float* conic_opacity, float* depths, float* rgb,
                               float* cov3D, uint32_t* tiles_touched, unsigned char* clamped) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,6 +212,12 @@ void launch_depth2normal(const float* depth, int W, int H, float fx, float fy, f
   dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
   // K^-1 entries computed on the host in float like torch.inverse of the float32 intrinsics
   k_depth2normal<<<grd, blk, 0, st>>>(depth, W, H, 1.0f / fx, 1.0f / fy, -cx / fx, -cy / fy, dmin, dmax, rot, out);
+}
+
+void launch_depth2point(const float* depth, int W, int H, float fx, float fy, float cx, float cy, const float* c2w,
+                        float* out, cudaStream_t st) {
+  dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
+  k_depth2point<<<grd, blk, 0, st>>>(depth, W, H, 1.0f / fx, 1.0f / fy, -cx / fx, -cy / fy, c2w, out);
 }
 
 void launch_debug_export(int P, int W, int H, long long R, GeomView g, BinView b, ImageView im,
@@ -405,6 +434,13 @@ int gsr_depth2normal(const float* depth, int width, int height, float fx, float 
   if (width <= 0 || height <= 0) return 0;
   { Prof pf(7, (cudaStream_t)stream); launch_depth2normal(depth, width, height, fx, fy, cx, cy, d_min, d_max, rot, out, (cudaStream_t)stream); }
   return check(cudaGetLastError(), "depth2normal") ? 0 : -1;
+}
+
+int gsr_depth2point(const float* depth, int width, int height, float fx, float fy, float cx, float cy,
+                    const float* cam_to_world, float* out, void* stream) {
+  if (width <= 0 || height <= 0) return 0;
+  launch_depth2point(depth, width, height, fx, fy, cx, cy, cam_to_world, out, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "depth2point") ? 0 : -1;
 }
 
 int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_buffer, const char* binning_buffer,

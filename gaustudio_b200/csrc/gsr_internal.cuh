@@ -112,6 +112,8 @@ void launch_mark_visible(int P, const float* means3D, const float* view, const f
                          unsigned char* present, cudaStream_t st);
 void launch_depth2normal(const float* depth, int W, int H, float fx, float fy, float cx, float cy, float dmin,
                          float dmax, const float* rot, float* out, cudaStream_t st);
+void launch_depth2point(const float* depth, int W, int H, float fx, float fy, float cx, float cy, const float* c2w,
+                        float* out, cudaStream_t st);
 void launch_debug_export(int P, int W, int H, long long R, GeomView g, BinView b, ImageView im,
                          uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib, float* final_T,
                          float* means2D, float* conic_opacity, float* depths, float* rgb, float* cov3D,

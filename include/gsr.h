@@ -115,6 +115,12 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 int gsr_depth2normal(const float* depth, int width, int height, float fx, float fy, float cx, float cy,
                      float d_min, float d_max, const float* rot, float* out, void* stream);
 
+/* Depth -> 3-D points (Camera.depth2point, gaustudio/datasets/__init__.py:307-339; the step after the path in
+ * gaustudio/scripts/extract_mesh.py:95-115).  out: device float[H*W*3]; cam_to_world: optional device float[16]
+ * (row-major inverse(extrinsics)) for coordinate='world', NULL for camera coordinates. */
+int gsr_depth2point(const float* depth, int width, int height, float fx, float fy, float cx, float cy,
+                    const float* cam_to_world, float* out, void* stream);
+
 /* Introspection for parity tests: copies internal state of the last forward out of the opaque buffers into
  * caller-provided DEVICE arrays (any may be NULL):
  *   point_list  uint32[R]   Gaussian index per sorted tile instance (== BinningState::point_list)

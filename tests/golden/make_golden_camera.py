@@ -56,6 +56,8 @@ for i in range(4):
                 f"c{i}_view": cam.world_view_transform.numpy(), f"c{i}_proj": cam.full_proj_transform.numpy(),
                 f"c{i}_center": cam.camera_center.numpy(), f"c{i}_K": cam.intrinsics.numpy(),
                 f"c{i}_depth": depth.numpy(), f"c{i}_normal_cam": cam.depth2normal(depth).numpy(),
-                f"c{i}_normal_world": cam.depth2normal(depth, coordinate="world").numpy()})
+                f"c{i}_normal_world": cam.depth2normal(depth, coordinate="world").numpy(),
+                f"c{i}_point_cam": cam.depth2point(depth).numpy(),
+                f"c{i}_point_world": cam.depth2point(depth, coordinate="world").numpy()})
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "camera_golden.npz"), **out)
 print("wrote camera_golden.npz", len(out), "arrays")

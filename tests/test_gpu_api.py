@@ -85,6 +85,14 @@ def test_mark_visible_and_depth2normal_against_oracle():
         assert float((nw.cpu() - torch.tensor(G[f"c{i}_normal_world"])).abs().max()) < 1e-4
         nt = ref_torch_ops.depth2normal(d, torch.tensor(K))
         assert float((n - nt).abs().max()) < 1e-4
+        # Camera.depth2point, camera and world coordinates (extract_mesh.py path)
+        pc = ops.depth2point(d, K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+        ref_c = torch.tensor(G[f"c{i}_point_cam"])
+        assert float((pc.cpu() - ref_c).abs().max()) <= 1e-5 * float(ref_c.abs().max())
+        c2w = torch.inverse(torch.tensor(ext))
+        pw = ops.depth2point(d, K[0, 0], K[1, 1], K[0, 2], K[1, 2], cam_to_world=c2w)
+        ref_w = torch.tensor(G[f"c{i}_point_world"])
+        assert float((pw.cpu() - ref_w).abs().max()) <= 2e-5 * float(ref_w.abs().max())
 
 
 def test_camera_depth2normal_on_rendered_depth():
