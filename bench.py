@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=3,
                     help="independent views alternate over this many CUDA streams (the library is stream-aware; the "
                          "reference launches on the legacy default stream and cannot overlap views)")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="replay each view's render+loss+backward+normal as one CUDA graph (gaustudio_b200.graphs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -175,16 +177,22 @@ def make_step(impl, model, dev, H, W, fused=True):
         def normal(cam, depth):
             return ref_torch_ops.depth2normal(depth, cam.K)
 
+    def loss_fn(out):
+        return F.l1_loss(out["render"], tc) + 0.1 * F.l1_loss(out["rendered_depth"], td) + \
+            0.1 * F.l1_loss(out["rendered_final_opacity"], to)
+
     def step(cam):
         for p in params:
             p.grad = None
         out = render(cam)
-        loss = F.l1_loss(out["render"], tc) + 0.1 * F.l1_loss(out["rendered_depth"], td) + \
-            0.1 * F.l1_loss(out["rendered_final_opacity"], to)
+        loss = loss_fn(out)
         loss.backward()
         n = normal(cam, out["rendered_depth"].detach()[0])
         return loss.detach() + 0.0 * n[0, 0, 0]
 
+    step.loss_fn = loss_fn
+    step.normal = normal
+    step.renderer = renderer if impl == "new" else None
     return step
 
 
@@ -268,10 +276,36 @@ def main():
     main_stream = torch.cuda.current_stream(dev)
     streams = [torch.cuda.Stream(dev) for _ in range(nstreams)] if nstreams > 1 else [main_stream]
 
+    # one CUDA graph per stream: render + loss + backward + depth->normal of a view become a single launch
+    graphed = None
+    if a.impl == "new" and a.graph:
+        try:
+            from gaustudio_b200.graphs import GraphedViewStep
+            fx, fy, cx, cy = hcams[0].fx, hcams[0].fy, hcams[0].cx, hcams[0].cy
+            post = lambda cam, out: step.normal(hcams[0], out["rendered_depth"].detach()[0])
+            sample = [hc.upload(dev) for hc in hcams[:: max(1, len(hcams) // 6)]]
+            first = GraphedViewStep(step.renderer, model, step.loss_fn, sample, post_fn=post)
+            graphed = [first] + [GraphedViewStep(step.renderer, model, step.loss_fn, sample[:1], capacity=first.capacity,
+                                                 post_fn=post) for _ in range(nstreams - 1)]
+        except Exception as ex:  # noqa: BLE001  (capture not possible here: fall back to eager launches)
+            print(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
+            graphed = None
+            _C.set_pipelined(bool(a.pipelined))
+
+    def run_step(i, cam):
+        if graphed is None:
+            return step(cam)
+        gs = graphed[i % nstreams]
+        return gs(cam) + 0.0 * gs.extra[0, 0, 0]
+
+    class PinnedCam:  # camera whose matrices are still in pinned host memory (e2e leg: the copy is the step's H2D)
+        def __init__(self, hc):
+            self.world_view_transform, self.full_proj_transform, self.camera_center = hc.h_view, hc.h_proj, hc.h_pos
+
     # ---------------- warm-up (W >= 3 per stream) ----------------
     for i in range(max(Wn, 3 * nstreams)):
         with torch.cuda.stream(streams[i % nstreams]):
-            step(hcams[i % len(hcams)].upload(dev))
+            run_step(i, hcams[i % len(hcams)].upload(dev))
     sync_all()
 
     # ---------------- leg 1: device-resident inputs ("value") ----------------
@@ -290,7 +324,7 @@ def main():
             st.wait_stream(main_stream)
     for i in range(K):
         with torch.cuda.stream(streams[i % nstreams]):
-            losses[i] = step(hcams[Wn + i])
+            losses[i] = run_step(i, hcams[Wn + i])
     if nstreams > 1:
         for st in streams:
             main_stream.wait_stream(st)
@@ -309,6 +343,8 @@ def main():
     # stalled the launch path on these hosts (value dropped 4x), each alone did not. ----------------
     stage_ms = None
     if a.impl == "new":
+        if graphed is not None:
+            _C.set_pipelined(bool(a.pipelined))  # eager launches for the per-kernel events
         L.gsr_profile_enable(1)
         for i in range(K):
             step(hcams[Wn + i])
@@ -318,6 +354,8 @@ def main():
         L.gsr_profile_enable(0)
         stage_ms = {STAGES[i]: (ms[i] / cn[i] if cn[i] else 0.0) for i in range(8)}
         _C.check_pipeline(wait=True)
+        if graphed is not None:
+            _C.set_pipelined(True, fixed_capacity=graphed[0].capacity)
 
     # ---------------- leg 2: end to end through the public API with host buffers ("e2e") ----------------
     host_loss = torch.zeros(K).pin_memory()      # pinned ring: one slot per step
@@ -332,8 +370,9 @@ def main():
             st.wait_stream(main_stream)
     for i in range(K):
         with torch.cuda.stream(streams[i % nstreams]):
-            hc = hcams[Wn + i].upload(dev)                          # H2D of this step's inputs from pinned memory
-            host_loss[i:i + 1].copy_(step(hc).reshape(1), non_blocking=True)   # D2H of the step's result ...
+            # H2D of this step's inputs from pinned memory (graph mode: straight into the graph's static tensors)
+            hc = PinnedCam(hcams[Wn + i]) if graphed is not None else hcams[Wn + i].upload(dev)
+            host_loss[i:i + 1].copy_(run_step(i, hc).reshape(1), non_blocking=True)   # D2H of the step's result ...
             done[i].record()
         if i >= lag:                                                # ... consumed `lag` steps later, like a trainer
             done[i - lag].synchronize()                             # logging its loss: the GPU never waits for the host
@@ -350,6 +389,10 @@ def main():
     ms_e2e = parallel.barrier_max_ms(e2.elapsed_time(e3), dev) if a.impl == "new" else e2.elapsed_time(e3)
     if a.impl == "new":
         _C.check_pipeline(wait=True)
+        if graphed is not None:
+            worst = max(g.max_rendered() for g in graphed)
+            if worst > graphed[0].capacity:
+                raise RuntimeError(f"a view needed {worst} tile instances, graph capacity is {graphed[0].capacity}")
 
     if world > 1 and torch.distributed.is_initialized() and rank != 0:
         torch.distributed.barrier()
@@ -422,6 +465,8 @@ def main():
                                "fwd+bwd (L1 colour + 0.1 L1 depth + 0.1 L1 opacity) + depth->normal",
                    "views_total": nviews_total, "parallelism": f"view-sharded x{world}",
                    "streams_per_gpu": nstreams,
+                   "launch": ("one CUDA graph per view (render+loss+backward+normal), fixed binning capacity "
+                              f"{graphed[0].capacity}" if graphed is not None else "eager kernel launches"),
                    "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 66 MB of per-view outputs vs 126 MB)",
                    "activations": ("fused into the projection kernel (fused_activations=True)" if a.fused and
                                    a.impl == "new" else "torch ops per view (reference op sequence)"),

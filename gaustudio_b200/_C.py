@@ -18,8 +18,12 @@ from . import _lib
 _pipeline = threading.local()
 
 
-def set_pipelined(enabled, slack=1.25):
+def set_pipelined(enabled, slack=1.25, fixed_capacity=None):
+    """enabled: sync-free forward.  fixed_capacity: always size the binning buffer for exactly this many tile
+    instances and keep NO host-side bookkeeping (no events, no pinned read-back) -- the mode CUDA-graph capture
+    needs (gaustudio_b200.graphs); the caller checks `num_rendered <= capacity` on the device side."""
     _pipeline.enabled = bool(enabled)
+    _pipeline.fixed = int(fixed_capacity) if fixed_capacity else 0
     _pipeline.slack = float(slack)
     _pipeline.hw = {}
     _pipeline.pending = []
@@ -140,7 +144,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     pl = _pl()
     cap, host = 0, None
     key = (dev.index, P, W, H)
-    if pl.enabled:
+    if pl.enabled and pl.fixed:
+        cap = pl.fixed
+    elif pl.enabled:
         check_pipeline()
         cap = pl.hw.get(key, 0)
         if cap > 0:
@@ -167,7 +173,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                     _ptr(campos), *tail)
         if r < 0:
             raise RuntimeError("gsr_forward failed: " + _lib.last_error())
-        if pl.enabled:
+        if pl.enabled and not pl.fixed:
             if cap > 0:
                 ev = torch.cuda.Event()
                 ev.record(stream)

@@ -1,0 +1,97 @@
+"""CUDA-graph capture of a whole per-view step (render -> loss -> backward [-> post]).
+
+Every launch of the library has a grid that depends only on the number of Gaussians and the image size -- the
+per-view instance count R stays on the device -- so in fixed-capacity mode the complete forward + backward is
+capturable: one `cudaGraphLaunch` per view instead of ~45 kernel launches and ~35 framework ops, which makes the
+throughput independent of host speed.  (The reference reads R back to the host inside every forward,
+rasterizer_impl.cu:284, and launches on the legacy default stream: it cannot be captured.)
+
+All replayed cameras must share image size and field of view (they are kernel parameters baked into the graph);
+the camera matrices live in static device tensors that `__call__` refreshes before each replay.
+"""
+import torch
+
+from . import _C
+
+
+class _StaticCamera:
+    def __init__(self, cam, dev):
+        self.FoVx, self.FoVy = cam.FoVx, cam.FoVy
+        self.image_width, self.image_height = cam.image_width, cam.image_height
+        self.world_view_transform = cam.world_view_transform.to(dev).clone()
+        self.full_proj_transform = cam.full_proj_transform.to(dev).clone()
+        self.camera_center = cam.camera_center.to(dev).clone()
+
+    def load(self, cam):
+        self.world_view_transform.copy_(cam.world_view_transform, non_blocking=True)
+        self.full_proj_transform.copy_(cam.full_proj_transform, non_blocking=True)
+        self.camera_center.copy_(cam.camera_center, non_blocking=True)
+
+
+class GraphedViewStep:
+    """step = GraphedViewStep(renderer, model, loss_fn, example_cameras, capacity=None, post_fn=None)
+    loss = step(camera)      # gradients of the model parameters are in their (static) .grad tensors
+
+    `capacity`: binning capacity (tile instances) baked into the graph; default = 1.3 x the largest count seen on
+    `example_cameras` (rendered eagerly once each).  `step.max_rendered()` returns the largest count any replay
+    needed -- compare it with `step.capacity` (an overflowing view is rendered incompletely, never out of bounds).
+
+    Create it BEFORE running an eager backward on the same parameter tensors: autograd binds a leaf's gradient
+    accumulator to the stream of its first backward, and a legacy-default-stream binding is illegal under capture
+    (cudaErrorStreamCaptureImplicit).  Eager steps after the capture are fine."""
+
+    def __init__(self, renderer, model, loss_fn, example_cameras, capacity=None, post_fn=None, device=None):
+        dev = device or model._xyz.device
+        self.dev, self.model = dev, model
+        cams = list(example_cameras)
+        if capacity is None:  # largest instance count over the example views (eager, exact mode) + 30 %
+            _C.set_pipelined(False)
+            worst = max(self._count(renderer, cam, model, dev) for cam in cams)
+            capacity = _C._quantise(worst, 1.3)
+        self.capacity = int(capacity)
+        self.cam = _StaticCamera(cams[0], dev)
+        self.rmax = torch.zeros(1, dtype=torch.int64, device=dev)
+        params = model.parameters_list()
+        _C.set_pipelined(True, fixed_capacity=self.capacity)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+
+        def body():
+            out = renderer.render(self.cam, model)
+            loss = loss_fn(out)
+            # the header of the opaque image buffer starts with num_rendered (uint64): track its maximum on device
+            img = out["render"].grad_fn.saved_tensors[-1]
+            self.rmax.copy_(torch.maximum(self.rmax, img[:8].view(torch.int64)))
+            loss.backward()
+            extra = post_fn(self.cam, out) if post_fn is not None else None
+            return loss.detach(), extra
+
+        with torch.cuda.stream(side):
+            for _ in range(3):  # warm-up outside capture (allocator, lazy module loads)
+                for p in params:
+                    p.grad = None
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.extra = body()
+        self.grads = [p.grad for p in params]
+        self.rmax.zero_()
+
+    @staticmethod
+    def _count(renderer, cam, model, dev):
+        """num_rendered of one eager (exact-mode) forward."""
+        out = renderer.render(_StaticCamera(cam, dev), model)
+        fn = out["render"].grad_fn
+        return int(fn.num_rendered) if fn is not None else 0
+
+    def __call__(self, camera):
+        self.cam.load(camera)
+        self.graph.replay()
+        return self.loss
+
+    def max_rendered(self):
+        return int(self.rmax.item())
