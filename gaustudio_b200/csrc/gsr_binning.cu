@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     const unsigned dmin = sh.dmin, span = sh.dmax - dmin;
     // bucket = floor((d - dmin) * NB / (span + 1)) via a 32-bit fixed-point reciprocal (span >= NB here), or the
     // identity when the tile's keys span fewer values than there are buckets
-    // a bucket costs one 15-step warp network however few entries it holds, so aim at ~20 entries per bucket
-    const unsigned nb = min((unsigned)NB, max(8u, n / 20u));
+    // one warp sorts one bucket: aim at ~24 entries per bucket (full lanes, rare spill beyond 64)
+    const unsigned nb = min((unsigned)NB, max(8u, n / 24u));
     const bool direct = span < nb;
     const unsigned mult = direct ? 0u : (unsigned)(((u64)nb << 32) / ((u64)span + 1ull));
     auto bucket = [=](u64 key) {
@@ -274,9 +274,22 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     for (unsigned bk = warp; bk < nb; bk += SORT_WARPS) {
       const unsigned s0 = sh.start[bk], m = sh.start[bk + 1] - s0;
       if (m <= 1) continue;
-      if (m <= 32) {
-        const u64 key = warp_sort32(lane < m ? B[s0 + lane] : ~0ull, lane);
-        if (lane < m) B[s0 + lane] = key;
+      if (m <= 64) {
+        // rank sort, up to two entries per lane: entries are distinct 64-bit values, so an entry's position is
+        // the number of smaller ones (m broadcast reads + compares: cheaper than a bitonic network for the
+        // ~24-entry buckets the split aims at)
+        const u64 k0 = lane < m ? B[s0 + lane] : ~0ull;
+        const u64 k1 = lane + 32 < m ? B[s0 + 32 + lane] : ~0ull;
+        unsigned r0 = 0, r1 = 0;
+        for (unsigned j = 0; j < m; j++) {
+          const u64 o = B[s0 + j];
+          r0 += (o < k0) ? 1u : 0u;
+          r1 += (o < k1) ? 1u : 0u;
+        }
+        __syncwarp();
+        if (lane < m) B[s0 + r0] = k0;
+        if (lane + 32 < m) B[s0 + r1] = k1;
+        __syncwarp();
       } else {
         warp_sort_mem(B + s0, m, lane);
       }
