@@ -20,8 +20,6 @@
 // the (non-deterministic) arrival order of the level-1 scatter.
 #include "gsr_internal.cuh"
 
-#include <cstdio>
-#include <cstdlib>
 
 namespace gsr {
 
@@ -189,7 +187,7 @@ template <int NB> struct SortShared {
 // CAP: entries held in shared memory; MIN_N: tiles up to MIN_N entries belong to the other launch;
 // NB: depth buckets of the MSD split (about 8 entries per bucket at CAP).
 template <int CAP, int MIN_N, int NB>
-__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b, int dbg_mode) {
+__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b) {
   extern __shared__ __align__(16) u64 sort_smem[];
   __shared__ SortShared<NB> sh;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -205,9 +203,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
   uint32_t* out = b.point_list + range.x;
   const u64* sorted;
 
-  if (dbg_mode == 1) {
-    sorted = seg;  // timing experiment: no sort
-  } else if (n <= 32) {
+  if (n <= 32) {
     // a single warp sorts the whole tile in registers
     if (warp == 0) {
       const u64 key = warp_sort32(lane < n ? seg[lane] : ~0ull, lane);
@@ -298,7 +294,6 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     sorted = B;
   }
   // the sorted order, as Gaussian indices (what the render kernels walk)
-  if (dbg_mode == 2) continue;
   for (unsigned i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)sorted[i];
   }
 }
@@ -312,13 +307,12 @@ void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, c
 }
 
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
-  static const int dbg_mode = getenv("GSR_SORT_DEBUG") ? atoi(getenv("GSR_SORT_DEBUG")) : 0;  // timing experiments only
   auto small = k_tile_sort<SORT_CAP_SMALL, 0, 512>;
   auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_SMALL, 2048>;
   constexpr int smem_small = SORT_CAP_SMALL * 8, smem_big = SORT_CAP_BIG * 8;
   cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);  // per device
-  small<<<T, SORT_THREADS, smem_small, st>>>(g, im, b, dbg_mode);
-  big<<<148, SORT_THREADS, smem_big, st>>>(g, im, b, dbg_mode);  // one CTA per SM, loops over hdr->num_big tiles
+  small<<<T, SORT_THREADS, smem_small, st>>>(g, im, b);
+  big<<<148, SORT_THREADS, smem_big, st>>>(g, im, b);  // one CTA per SM, loops over hdr->num_big tiles
 }
 
 }  // namespace gsr

@@ -41,15 +41,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// one elected thread: arm the barrier with the byte count, then launch the 1-D bulk copy (TMA)
-__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-  const unsigned b = smem_u32(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(b)
-               : "memory");
-}
 // asynchronous 16-byte global->shared copy (LDGSTS, L2 only) and its completion hook on an mbarrier
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
