@@ -92,9 +92,14 @@ size_t image_bytes(int W, int H) {
   const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
   return reinterpret_cast<size_t>(im.big_tiles + T) + 512;
 }
+// The binning arrays are laid out for the instance count rounded up to 1 Mi entries: the buffer size (and with
+// it the caller's allocator block) then takes only a few distinct values across views instead of one per view.
+static inline long long round_cap(long long n) { return (n + (1ll << 20) - 1) & ~((1ll << 20) - 1); }
+
 BinView carve_binning(char* base, long long cap) {
   BinView b;
   char* p = base;
+  cap = round_cap(cap);
   take(p, b.ents, (size_t)cap);
   take(p, b.ents2, (size_t)cap);
   take(p, b.point_list, (size_t)cap + 16);
@@ -102,7 +107,7 @@ BinView carve_binning(char* base, long long cap) {
 }
 size_t binning_bytes(long long R) {
   BinView b = carve_binning(nullptr, R);
-  return reinterpret_cast<size_t>(b.point_list + (size_t)R + 16) + 512;
+  return reinterpret_cast<size_t>(b.point_list + (size_t)round_cap(R) + 16) + 512;
 }
 
 namespace {

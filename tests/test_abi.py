@@ -34,7 +34,8 @@ def test_host_only_entry_points():
     assert L.gsr_geometry_bytes(1_000_000) < 140 * 1_000_000  # ~137 B per Gaussian of forward+backward state
     i1 = L.gsr_image_bytes(1920, 1080)
     assert 8 * 1920 * 1080 <= i1 < 9 * 1920 * 1080 + 1_000_000
-    assert L.gsr_binning_bytes(0) >= 0 and 20 * 10**6 <= L.gsr_binning_bytes(10**6) < 21 * 10**6  # 20 B per instance
+    assert L.gsr_binning_bytes(0) >= 0 and 20 * 2**20 <= L.gsr_binning_bytes(10**6) < 21 * 2**20  # 20 B per instance, 1 Mi granules
+    assert L.gsr_binning_bytes(2**20 + 1) > L.gsr_binning_bytes(2**20) == L.gsr_binning_bytes(2**20 - 5)
     assert isinstance(_lib.last_error(), str)
 
 
