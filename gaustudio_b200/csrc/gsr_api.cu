@@ -283,6 +283,7 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
   a.prefiltered = prefiltered; a.radii_out = radii;
   a.fused = fused; a.f_dc = f_dc; a.f_rest = f_rest;
   a.sh_bulk = fused && M > 1 && ((reinterpret_cast<size_t>(f_dc) | reinterpret_cast<size_t>(f_rest)) & 15) == 0;
+  a.sh_rows = !fused && shs && M == 16 && (reinterpret_cast<size_t>(shs) & 15) == 0;
 
   const unsigned long long cap0 = r_capacity > 0 ? (unsigned long long)r_capacity : ~0ull;
   if (!check(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * T * SUBBINS, st), "memset tile_count")) return -1;
@@ -360,6 +361,8 @@ static int backward_impl(int fused, const float* f_dc, const float* f_rest, cons
   a.dL_df_dc = dL_df_dc; a.dL_df_rest = dL_df_rest;
   a.sh_bulk = fused && M > 1 && ((reinterpret_cast<size_t>(f_dc) | reinterpret_cast<size_t>(f_rest) |
                                   reinterpret_cast<size_t>(dL_df_dc) | reinterpret_cast<size_t>(dL_df_rest)) & 15) == 0;
+  a.sh_rows = !fused && shs && dL_dsh && M == 16 &&
+              ((reinterpret_cast<size_t>(shs) | reinterpret_cast<size_t>(dL_dsh)) & 15) == 0;
   { Prof pf(6, st); launch_preprocess_bwd(a, g, st); }
   if (!stage_ok(dbg, st, "preprocess_bwd")) return -1;
   return 0;

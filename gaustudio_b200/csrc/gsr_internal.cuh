@@ -80,6 +80,7 @@ struct FwdArgs {
   int fused;
   const float *f_dc, *f_rest;
   int sh_bulk;  // f_dc / f_rest are 16-byte aligned: stage each CTA's contiguous SH block with TMA bulk copies
+  int sh_rows;  // un-fused [P,16,3] SH tensor, 16-byte aligned: every thread stages its own 192-byte row with TMA
 };
 
 // ---- launch wrappers (each enqueues on `st`) ----
@@ -106,6 +107,7 @@ struct BwdArgs {
   const float *f_dc, *f_rest, *opacities_raw;
   float *dL_df_dc, *dL_df_rest;
   int sh_bulk;  // as in FwdArgs; the SH gradient block leaves through a TMA bulk store as well
+  int sh_rows;  // as in FwdArgs; gradient rows leave through per-row bulk stores
 };
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st);
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,

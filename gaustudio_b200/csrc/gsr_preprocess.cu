@@ -32,6 +32,7 @@ struct V3 { float x, y, z; };
 // odd strides, so per-thread row reads are bank-conflict free.  The backward writes its SH gradients into the
 // same rows and ships the block with one bulk store per tensor.
 constexpr int PRE_THREADS = 256;
+constexpr int SH_ROW = 52;  // floats per staged row of the un-fused [P,16,3] tensor: 192 B of data + 16 B pad (16-B aligned rows)
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -45,6 +46,11 @@ __device__ __forceinline__ void bar_init_expect(unsigned long long* bar, unsigne
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// every thread of the CTA stages its own row: barrier expects PRE_THREADS arrivals, each announcing its bytes
+__device__ __forceinline__ void row_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  bulk_load(dst, src, bytes, bar);
 }
 __device__ __forceinline__ void bar_wait0(unsigned long long* bar) {
   asm volatile(
@@ -203,6 +209,15 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
     bulk_load(sh_stage + PRE_THREADS * 3, a.f_rest + (size_t)blockIdx.x * PRE_THREADS * rest_row, b_rest, &sh_bar);
   }
   if (bulk) __syncthreads();  // barrier initialised before anyone polls it
+  const bool rows = a.sh_rows && a.D > 0 && (blockIdx.x + 1) * PRE_THREADS <= a.P;
+  if (rows) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&sh_bar)), "r"(PRE_THREADS) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    row_load(sh_stage + threadIdx.x * SH_ROW, a.shs + (size_t)idx * 48, 192, &sh_bar);
+  }
   if (idx < a.P) {
     int radius_i = 0;
     uint32_t tiles = 0;
@@ -264,6 +279,10 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
               bar_wait0(&sh_bar);
               sh0 = sh_stage + threadIdx.x * 3;
               shr = sh_stage + PRE_THREADS * 3 + threadIdx.x * rest_row;
+            } else if (rows) {
+              bar_wait0(&sh_bar);
+              sh0 = sh_stage + threadIdx.x * SH_ROW;
+              shr = sh0 + 3;
             }
             const float ox = p.x - a.campos[0], oy = p.y - a.campos[1], oz = p.z - a.campos[2];
             const float len = sqrtf(__fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));  // glm::length
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
   for_each_tile(x0, y0, x1, y1, a.gx, [&](int tile, unsigned src) {
     atomicAdd(&im.tile_count[subbin_of(warp_base + (int)src) * T + tile], 1u);
   });
-  if (bulk && threadIdx.x == 0) bar_wait0(&sh_bar);  // the copies must have landed before the CTA retires
+  if ((bulk || rows) && threadIdx.x == 0) bar_wait0(&sh_bar);  // the copies must have landed before the CTA retires
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,9 +371,17 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
       bulk_load(sh_stage + PRE_THREADS * 3, a.f_rest + (size_t)blockIdx.x * PRE_THREADS * rest_row, b_rest, &sh_bar);
     }
     __syncthreads();
-  } else if (idx >= a.P) {
-    return;
   }
+  const bool rows = a.sh_rows && (blockIdx.x + 1) * PRE_THREADS <= a.P;
+  if (rows) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&sh_bar)), "r"(PRE_THREADS) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    row_load(sh_stage + threadIdx.x * SH_ROW, a.shs + (size_t)idx * 48, 192, &sh_bar);
+  }
+  if (!bulk && !rows && idx >= a.P) return;
   const bool vis = a.radii[idx] > 0;  // quirk 8
   const float4* ga = reinterpret_cast<const float4*>(g.grad + (size_t)idx * GRAD_F);
   float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
@@ -387,6 +414,10 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
     bar_wait0(&sh_bar);
     dsh0 = sh_stage + threadIdx.x * 3;
     dshr = sh_stage + PRE_THREADS * 3 + threadIdx.x * rest_row;
+  } else if (rows) {
+    bar_wait0(&sh_bar);
+    dsh0 = sh_stage + threadIdx.x * SH_ROW;
+    dshr = dsh0 + 3;
   }
   auto dsh_zero = [&](int from) {
     if (!dsh0) return;
@@ -461,8 +492,8 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
 
     if (have_sh) {
       // SH backward, backward.cu:20-139
-      const float* sh0 = bulk ? dsh0 : (a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * M * 3);
-      const float* shr = bulk ? dshr : (a.fused ? a.f_rest + (size_t)idx * (M - 1) * 3 : sh0 + 3);
+      const float* sh0 = (bulk || rows) ? dsh0 : (a.fused ? a.f_dc + (size_t)idx * 3 : a.shs + (size_t)idx * M * 3);
+      const float* shr = (bulk || rows) ? dshr : (a.fused ? a.f_rest + (size_t)idx * (M - 1) * 3 : sh0 + 3);
       const float ox = mean.x - a.campos[0], oy = mean.y - a.campos[1], oz = mean.z - a.campos[2];
       const float len = sqrt(ox * ox + oy * oy + oz * oz);
       const float x = ox / len, y = oy / len, z = oz / len;
@@ -574,6 +605,12 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released after this
     }
+  } else if (rows) {
+    // each thread ships the gradient row it wrote itself: its own generic-proxy writes -> async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bulk_store(a.dL_dsh + (size_t)idx * 48, sh_stage + threadIdx.x * SH_ROW, 192);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
@@ -589,12 +626,12 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const f
 }  // namespace
 
 void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st) {
-  const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : 0;
+  const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : (a.sh_rows ? (size_t)PRE_THREADS * SH_ROW * 4 : 0);
   if (smem > 48 * 1024 - 64) cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_preprocess_fwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g, im);
 }
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st) {
-  const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : 0;
+  const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : (a.sh_rows ? (size_t)PRE_THREADS * SH_ROW * 4 : 0);
   if (smem > 48 * 1024 - 64) cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_preprocess_bwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g);
 }
