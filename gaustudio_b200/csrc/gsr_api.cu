@@ -3,6 +3,7 @@
 // ($RAST/cuda_rasterizer/rasterizer_impl.cu:141-153, 198-343, 347-452) on top of the B200 kernels.
 #include "../../include/gsr.h"
 #include "gsr_internal.cuh"
+#include <cmath>
 
 #include <cstdio>
 #include <cstring>
@@ -127,34 +128,14 @@ __global__ void k_depth2normal(const float* __restrict__ depth, int W, int H, fl
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
   if (u >= W || v >= H) return;
   float* o = out + ((size_t)v * W + u) * 3;
-  bool valid = u > 0 && v > 0 && u < W - 1 && v < H - 1;
-  float n0 = -1.f, n1 = -1.f, n2 = -1.f;
-  if (valid) {
-    auto point = [&](int uu, int vv, float& x, float& y, float& z) {
-      z = depth[(size_t)vv * W + uu];
-      const float uz = __fmul_rn(__fmul_rn(__fdiv_rn((float)uu, (float)(W - 1)), (float)(W - 1)), z);
-      const float vz = __fmul_rn(__fmul_rn(__fdiv_rn((float)vv, (float)(H - 1)), (float)(H - 1)), z);
-      x = __fadd_rn(__fmul_rn(uz, ifx), __fmul_rn(z, ox));
-      y = __fadd_rn(__fmul_rn(vz, ify), __fmul_rn(z, oy));
-    };
-    float cx, cy, cz, tx, ty, tz, bx, by, bz, lx, ly, lz, rx, ry, rz;
-    point(u, v, cx, cy, cz); point(u, v - 1, tx, ty, tz); point(u, v + 1, bx, by, bz);
-    point(u - 1, v, lx, ly, lz); point(u + 1, v, rx, ry, rz);
-    auto ok = [&](float z) { return z > dmin && z < dmax; };
-    valid = ok(cz) && ok(tz) && ok(bz) && ok(lz) && ok(rz);
-    if (valid) {
-      const float ax = tx - bx, ay = ty - by, az = tz - bz, hx = lx - rx, hy = ly - ry, hz = lz - rz;
-      float c0 = -(__fmul_rn(ay, hz) - __fmul_rn(az, hy)), c1 = -(__fmul_rn(az, hx) - __fmul_rn(ax, hz)),
-            c2 = -(__fmul_rn(ax, hy) - __fmul_rn(ay, hx));
-      const float len = fmaxf(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e-12f);
-      c0 /= len; c1 /= len; c2 /= len;
-      if (rot) {
-        n0 = c0 * rot[0] + c1 * rot[3] + c2 * rot[6];
-        n1 = c0 * rot[1] + c1 * rot[4] + c2 * rot[7];
-        n2 = c0 * rot[2] + c1 * rot[5] + c2 * rot[8];
-      } else {
-        n0 = c0; n1 = c1; n2 = c2;
-      }
+  float n0 = -1.f, n1 = -1.f, n2 = -1.f, c0, c1, c2;
+  if (cross_normal(depth, u, v, W, H, ifx, ify, ox, oy, dmin, dmax, c0, c1, c2)) {
+    if (rot) {
+      n0 = c0 * rot[0] + c1 * rot[3] + c2 * rot[6];
+      n1 = c0 * rot[1] + c1 * rot[4] + c2 * rot[7];
+      n2 = c0 * rot[2] + c1 * rot[5] + c2 * rot[8];
+    } else {
+      n0 = c0; n1 = c1; n2 = c2;
     }
   }
   o[0] = n0; o[1] = n1; o[2] = n2;
@@ -449,6 +430,61 @@ int gsr_depth2point(const float* depth, int width, int height, float fx, float f
   if (width <= 0 || height <= 0) return 0;
   launch_depth2point(depth, width, height, fx, fy, cx, cy, cam_to_world, out, (cudaStream_t)stream);
   return check(cudaGetLastError(), "depth2point") ? 0 : -1;
+}
+
+int gsr_masked_bilateral(const float* depth, const unsigned char* mask, int width, int height, int d, float sigma_color,
+                         float sigma_space, float* out_depth, unsigned char* out_mask, unsigned int* scratch,
+                         void* stream) {
+  if (width <= 0 || height <= 0) return 0;
+  if (d < 1 || d > 15 || (d & 1) == 0) { g_err = "gsr_masked_bilateral: d must be odd, 1..15"; return -1; }
+  if (!depth || !mask || !out_depth || !out_mask || !scratch) { g_err = "gsr_masked_bilateral: null pointer"; return -1; }
+  // OpenCV: non-positive sigmas become 1; weights are evaluated in double and stored as float
+  const double sc = sigma_color <= 0 ? 1.0 : (double)sigma_color, ss = sigma_space <= 0 ? 1.0 : (double)sigma_space;
+  const double gauss_color = -0.5 / (sc * sc), gauss_space = -0.5 / (ss * ss);
+  const int r = d / 2;
+  SpaceKernel sk;
+  for (int i = 0; i < 225; i++) sk.w[i] = 0.f;
+  for (int dy = -r; dy <= r; dy++)
+    for (int dx = -r; dx <= r; dx++) {
+      const double rr = std::sqrt((double)dy * dy + (double)dx * dx);
+      if (rr > r || (dy == 0 && dx == 0)) continue;
+      sk.w[(dy + r) * (2 * r + 1) + dx + r] = (float)std::exp(rr * rr * gauss_space);
+    }
+  launch_masked_bilateral(depth, mask, width, height, r, (float)gauss_color, sk, out_depth, out_mask, scratch,
+                          (cudaStream_t)stream);
+  return check(cudaGetLastError(), "masked_bilateral") ? 0 : -1;
+}
+
+int gsr_extract_normals(const float* filtered_depth, const unsigned char* fg_mask, const float* opacity,
+                        const float* median_depth, int width, int height, float fx, float fy, float cx, float cy,
+                        const float* rot, float depth_limit, float opacity_min, float* cam_normals,
+                        float* neg_world_normals, unsigned char* valid, void* stream) {
+  if (width <= 0 || height <= 0) return 0;
+  if (!filtered_depth || !fg_mask || !opacity || !median_depth || !rot || !neg_world_normals || !valid) {
+    g_err = "gsr_extract_normals: null pointer"; return -1;
+  }
+  launch_extract_normals(filtered_depth, fg_mask, opacity, median_depth, width, height, fx, fy, cx, cy, rot, depth_limit,
+                         opacity_min, cam_normals, neg_world_normals, valid, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "extract_normals") ? 0 : -1;
+}
+
+int gsr_normal_fusion_pass(int64_t n, const int64_t* ids, const float* normals, const float* confidences, int P,
+                           const float* xyz, float cam_x, float cam_y, float cam_z, const float* mean_normals,
+                           float threshold, float* sum_normals, float* sum_weights, unsigned char* touched,
+                           void* stream) {
+  if (n <= 0) return 0;
+  if (!ids || !normals || !confidences || !xyz || !sum_normals || !sum_weights || P <= 0) {
+    g_err = "gsr_normal_fusion_pass: null pointer"; return -1;
+  }
+  launch_fusion_pass((long long)n, reinterpret_cast<const long long*>(ids), normals, confidences, P, xyz, cam_x, cam_y,
+                     cam_z, mean_normals, threshold, sum_normals, sum_weights, touched, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "normal_fusion_pass") ? 0 : -1;
+}
+
+int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean_normals, void* stream) {
+  if (P <= 0) return 0;
+  launch_fusion_mean(P, sum_normals, sum_weights, mean_normals, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "normal_fusion_mean") ? 0 : -1;
 }
 
 int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_buffer, const char* binning_buffer,

@@ -137,4 +137,46 @@ __device__ __forceinline__ void unpack_rect(uint2 r, int& xmin, int& ymin, int& 
   xmin = r.x & 0xffff; xmax = r.x >> 16; ymin = r.y & 0xffff; ymax = r.y >> 16;
 }
 
+// 5-point cross normal of Camera.depth2normal (gaustudio/datasets/__init__.py:106-112,307-380, k = 3), same
+// arithmetic order as the reference's torch ops:  u' = (u/(W-1))*(W-1);  X = (u'*z)*Kinv00 + z*Kinv02, ...;
+// n = -normalize(cross(top-bottom, left-right)).  False (no output) where the reference writes -1.
+__device__ __forceinline__ bool cross_normal(const float* __restrict__ depth, int u, int v, int W, int H, float ifx,
+                                             float ify, float ox, float oy, float dmin, float dmax, float& c0,
+                                             float& c1, float& c2) {
+  if (!(u > 0 && v > 0 && u < W - 1 && v < H - 1)) return false;
+  auto point = [&](int uu, int vv, float& x, float& y, float& z) {
+    z = depth[(size_t)vv * W + uu];
+    const float uz = __fmul_rn(__fmul_rn(__fdiv_rn((float)uu, (float)(W - 1)), (float)(W - 1)), z);
+    const float vz = __fmul_rn(__fmul_rn(__fdiv_rn((float)vv, (float)(H - 1)), (float)(H - 1)), z);
+    x = __fadd_rn(__fmul_rn(uz, ifx), __fmul_rn(z, ox));
+    y = __fadd_rn(__fmul_rn(vz, ify), __fmul_rn(z, oy));
+  };
+  float cx, cy, cz, tx, ty, tz, bx, by, bz, lx, ly, lz, rx, ry, rz;
+  point(u, v, cx, cy, cz); point(u, v - 1, tx, ty, tz); point(u, v + 1, bx, by, bz);
+  point(u - 1, v, lx, ly, lz); point(u + 1, v, rx, ry, rz);
+  auto ok = [&](float z) { return z > dmin && z < dmax; };
+  if (!(ok(cz) && ok(tz) && ok(bz) && ok(lz) && ok(rz))) return false;
+  const float ax = tx - bx, ay = ty - by, az = tz - bz, hx = lx - rx, hy = ly - ry, hz = lz - rz;
+  c0 = -(__fmul_rn(ay, hz) - __fmul_rn(az, hy));
+  c1 = -(__fmul_rn(az, hx) - __fmul_rn(ax, hz));
+  c2 = -(__fmul_rn(ax, hy) - __fmul_rn(ay, hx));
+  const float len = fmaxf(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e-12f);
+  c0 /= len; c1 /= len; c2 /= len;
+  return true;
+}
+
+// gsr_extract.cu -- the extraction post-pass (gaustudio/scripts/extract_pcd.py)
+struct SpaceKernel { float w[225]; };  // (2r+1)^2 spatial weights of the bilateral filter, 0 outside the disc
+void launch_masked_bilateral(const float* depth, const unsigned char* mask, int W, int H, int r, float gauss_color,
+                             const SpaceKernel& sk, float* out_depth, unsigned char* out_mask, unsigned* scratch,
+                             cudaStream_t st);
+void launch_extract_normals(const float* depth, const unsigned char* fg, const float* opacity, const float* median_depth,
+                            int W, int H, float fx, float fy, float cx, float cy, const float* rot, float depth_limit,
+                            float opacity_min, float* cam_normals, float* neg_world, unsigned char* valid,
+                            cudaStream_t st);
+void launch_fusion_pass(long long n, const long long* ids, const float* normals, const float* conf, int P,
+                        const float* xyz, float tx, float ty, float tz, const float* mean, float thresh,
+                        float* sum_normals, float* sum_weights, unsigned char* touched, cudaStream_t st);
+void launch_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean, cudaStream_t st);
+
 }  // namespace gsr

@@ -121,6 +121,44 @@ int gsr_depth2normal(const float* depth, int width, int height, float fx, float 
 int gsr_depth2point(const float* depth, int width, int height, float fx, float fy, float cx, float cy,
                     const float* cam_to_world, float* out, void* stream);
 
+/* ---- extraction post-pass: what gaustudio/scripts/extract_pcd.py runs on every rendered view ----
+ *
+ * masked_bilateral_filter (extract_pcd.py:185-238), which the reference executes on the CPU through OpenCV:
+ *   out_mask  = !dilate(!mask, d x d box)                              (cv2.dilate, default border)
+ *   out_depth = bilateralFilter((depth - min)/(max - min), d, sigma_color, sigma_space) * (max - min) + min
+ *               on out_mask pixels (min/max over them, masked-out pixels entering the filter as 0, disc support of
+ *               radius d/2, centre weight 1, REFLECT_101 border), the input depth elsewhere.
+ * depth/out_depth: device float[H*W]; mask/out_mask: device uint8[H*W] (torch.bool layout); d odd, 1..15;
+ * scratch: 2 device words owned by the caller (the depth range never visits the host). */
+int gsr_masked_bilateral(const float* depth, const unsigned char* mask, int width, int height, int d,
+                         float sigma_color, float sigma_space, float* out_depth, unsigned char* out_mask,
+                         unsigned int* scratch, void* stream);
+
+/* Per-view normal extraction (extract_pcd.py:325-335): cam = depth2normal(filtered_depth, 'camera') with -1 where
+ * !fg_mask; world = cam @ rot (rot = inverse(extrinsics[:3,:3]).t(), device float[9], applied to the -1 fill too,
+ * as normal2worldnormal does); valid = sum(world) > -3 && median_depth < depth_limit && opacity > opacity_min.
+ * Outputs: cam_normals float[H*W*3] (optional), neg_world_normals float[H*W*3] (= -world, what the fusion
+ * consumes), valid uint8[H*W]. */
+int gsr_extract_normals(const float* filtered_depth, const unsigned char* fg_mask, const float* opacity,
+                        const float* median_depth, int width, int height, float fx, float fy, float cx, float cy,
+                        const float* rot, float depth_limit, float opacity_min, float* cam_normals,
+                        float* neg_world_normals, unsigned char* valid, void* stream);
+
+/* One view of one accumulation pass of normal_fusion (extract_pcd.py:117-136 first pass, :143-165 second pass):
+ * for entry i with Gaussian id = ids[i]:  v = cam - xyz[id];  w = confidences[i] * |dot(v/|v|, n_i)| / (|v| + 1e-6);
+ * with mean_normals != NULL the entry is dropped unless |n_i - mean_normals[id]| < threshold;
+ * sum_normals[id] += n_i * w; sum_weights[id] += w; touched[id] = 1 (optional).  Accumulators are dense over the
+ * P Gaussians (the reference's torch.unique / inverse indices are `nonzero(touched)`), zeroed by the caller.
+ * (cam_x, cam_y, cam_z) is what the reference uses as the camera position: extrinsics[:3, 3]. */
+int gsr_normal_fusion_pass(int64_t n, const int64_t* ids, const float* normals, const float* confidences, int P,
+                           const float* xyz, float cam_x, float cam_y, float cam_z, const float* mean_normals,
+                           float threshold, float* sum_normals, float* sum_weights, unsigned char* touched,
+                           void* stream);
+
+/* mean_normals[i] = normalize(sum_normals[i] / sum_weights[i]) (extract_pcd.py:139-140,167-168; 0/0 stays NaN). */
+int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean_normals,
+                           void* stream);
+
 /* Introspection for parity tests: copies internal state of the last forward out of the opaque buffers into
  * caller-provided DEVICE arrays (any may be NULL):
  *   point_list  uint32[R]   Gaussian index per sorted tile instance (== BinningState::point_list)
