@@ -487,6 +487,19 @@ int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_wei
   return check(cudaGetLastError(), "normal_fusion_mean") ? 0 : -1;
 }
 
+int gsr_adam_step(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, int64_t step,
+                  int decoupled, float grad_scale, int zero_grad, void* stream) {
+  if (n_groups <= 0) return 0;
+  if (!groups || n_groups > GSR_ADAM_MAX_GROUPS) { g_err = "gsr_adam_step: 1..16 groups"; return -1; }
+  if (step < 1) { g_err = "gsr_adam_step: step counts from 1"; return -1; }
+  for (int i = 0; i < n_groups; i++)
+    if (groups[i].numel > 0 && (!groups[i].param || !groups[i].grad || !groups[i].exp_avg || !groups[i].exp_avg_sq)) {
+      g_err = "gsr_adam_step: null tensor in a group"; return -1;
+    }
+  launch_adam(n_groups, groups, beta1, beta2, eps, (long long)step, decoupled, grad_scale, zero_grad, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "adam_step") ? 0 : -1;
+}
+
 int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_buffer, const char* binning_buffer,
                      const char* image_buffer, uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib,
                      float* final_T, float* means2D, float* conic_opacity, float* depths, float* rgb, float* cov3D,

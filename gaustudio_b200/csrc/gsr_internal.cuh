@@ -178,5 +178,10 @@ void launch_fusion_pass(long long n, const long long* ids, const float* normals,
                         const float* xyz, float tx, float ty, float tz, const float* mean, float thresh,
                         float* sum_normals, float* sum_weights, unsigned char* touched, cudaStream_t st);
 void launch_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean, cudaStream_t st);
+}  // namespace gsr
+struct gsr_adam_group;
+namespace gsr {
+int launch_adam(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, long long step,
+                int decoupled, float grad_scale, int zero_grad, cudaStream_t st);
 
 }  // namespace gsr

@@ -1,0 +1,174 @@
+"""Optimizer plugin surface of the reference (gaustudio/pipelines/optimizers/{__init__,base,general_optimizer}.py)
+with the step itself on the device in ONE launch.
+
+    opt = optimizers.make({"name": "general", "model": pcd, "optimizer_name": "AdamW",
+                           "args": {"lr": 0.0, "eps": 1e-15},
+                           "params": {"xyz": {"lr": 1.6e-4}, "opacity": {"lr": 0.05}, ...}})   # configs/vanilla.yaml:30-46
+    loss.backward(); opt.step(); opt.zero_grad()
+
+`Adam` / `AdamW` run through `FusedAdam` (gsr_adam_step, include/gsr.h): every parameter group in one kernel,
+optionally with the gradient averaging of data-parallel training (`grad_scale`) and `zero_grad` fused in.  Any other
+`optimizer_name` is handed to `torch.optim` exactly as the reference does.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+
+optimizers = {}
+
+
+def register(name):
+    def decorator(cls):
+        optimizers[name] = cls
+        return cls
+    return decorator
+
+
+def make(config):
+    if isinstance(config, str):
+        name = config
+        config = {}
+    else:
+        name = config.get("name")
+    if not name:
+        raise ValueError("Optimizer name is required")
+    if name not in optimizers:
+        raise ValueError(f"Unknown optimizer: {name}")
+    return optimizers[name](config)
+
+
+class _AdamGroup(C.Structure):  # gsr_adam_group, include/gsr.h
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float)]
+
+
+MAX_GROUPS = 16
+
+
+class FusedAdam:
+    """torch.optim.Adam / AdamW semantics (no amsgrad, no maximize) with the whole step in one CUDA launch.
+    `param_groups` follows torch: an iterable of tensors or of dicts {'params': tensor | [tensors], 'lr': ..., ...}."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, decoupled=True, **unsupported):
+        if unsupported.get("amsgrad") or unsupported.get("maximize"):
+            raise ValueError("FusedAdam: amsgrad / maximize are not supported")
+        if weight_decay is None:
+            weight_decay = 1e-2 if decoupled else 0.0  # torch defaults: AdamW 0.01, Adam 0
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.decoupled = bool(decoupled)
+        params = list(params)
+        if params and not isinstance(params[0], dict):
+            params = [{"params": params}]
+        self.param_groups = []
+        for g in params:
+            g = dict(g)
+            ps = g["params"]
+            g["params"] = [ps] if isinstance(ps, torch.Tensor) else list(ps)
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
+            self.param_groups.append(g)
+        betas_eps = {(g["betas"], g["eps"]) for g in self.param_groups}
+        if len(betas_eps) > 1:
+            raise ValueError("FusedAdam: betas and eps must be the same for every group (one launch)")
+        self.state = {}
+        self.step_count = 0
+
+    def _tensors(self):
+        for g in self.param_groups:
+            for p in g["params"]:
+                yield g, p
+
+    def step(self, grad_scale=1.0, zero_grad=False, closure=None):
+        """One optimizer step over every parameter that has a gradient.  grad_scale multiplies the gradients first
+        (1/world_size after a summing all-reduce); zero_grad=True leaves the gradients zeroed by the same kernel."""
+        if closure is not None:
+            raise ValueError("FusedAdam: closures are not supported")
+        rows, keep = [], []
+        dev = None
+        for g, p in self._tensors():
+            if p.grad is None:
+                continue
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("FusedAdam needs contiguous float32 CUDA parameters (there is no CPU path)")
+            grad = p.grad
+            if not grad.is_contiguous():
+                grad = p.grad = grad.contiguous()
+            st = self.state.get(p)
+            if st is None:
+                st = self.state[p] = {"exp_avg": torch.zeros_like(p, memory_format=torch.contiguous_format),
+                                      "exp_avg_sq": torch.zeros_like(p, memory_format=torch.contiguous_format)}
+            dev = p.device
+            rows.append(_AdamGroup(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                   p.numel(), float(g["lr"]), float(g["weight_decay"])))
+            keep.append(grad)
+        if not rows:
+            return
+        self.step_count += 1
+        b1, b2 = self.param_groups[0]["betas"]
+        eps = self.param_groups[0]["eps"]
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for i in range(0, len(rows), MAX_GROUPS):
+                chunk = rows[i:i + MAX_GROUPS]
+                arr = (_AdamGroup * len(chunk))(*chunk)
+                rc = L.gsr_adam_step(len(chunk), C.cast(arr, C.c_void_p), float(b1), float(b2), float(eps), self.step_count,
+                                     int(self.decoupled), float(grad_scale), int(bool(zero_grad)), stream)
+                if rc < 0:
+                    raise RuntimeError("gsr_adam_step failed: " + _lib.last_error())
+
+    def zero_grad(self, set_to_none=False):
+        """Keeps the gradient tensors by default (the flat all-reduce bucket of parallel.GradBucket aliases them)."""
+        for _, p in self._tensors():
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()
+
+
+class BaseOptimizer:
+    """gaustudio/pipelines/optimizers/base.py:7-34."""
+
+    def __init__(self, config, **kwargs):
+        self.config = config
+        self.model = config["model"]
+        self._initialize_internal_state()
+        self.setup_optimizer()
+
+    def setup_optimizer(self):
+        name = self.config["optimizer_name"]
+        args = dict(self.config.get("args") or {})
+        if name in ("Adam", "AdamW"):
+            self._optimizer = FusedAdam(self.param_groups, decoupled=(name == "AdamW"), **args)
+        else:
+            self._optimizer = getattr(torch.optim, name)(self.param_groups, **args)
+
+    def _initialize_internal_state(self):
+        raise NotImplementedError
+
+    def step(self, **kw):
+        self._optimizer.step(**kw)
+
+    def zero_grad(self):
+        self._optimizer.zero_grad()
+
+
+@register("general")
+class GeneralOptimizer(BaseOptimizer):
+    """gaustudio/pipelines/optimizers/general_optimizer.py:9-21: one group per entry of config['params'] (the model
+    attribute `_<name>` becomes an nn.Parameter), else every model parameter in one group."""
+
+    def _initialize_internal_state(self):
+        if "params" in self.config:
+            self.param_groups = []
+            for name, args in self.config["params"].items():
+                parameter = nn.Parameter(getattr(self.model, "_" + name))
+                parameter.requires_grad = True
+                setattr(self.model, "_" + name, parameter)
+                self.param_groups.append({"params": getattr(self.model, "_" + name), "name": name, **(args or {})})
+        else:
+            self.param_groups = self.model.parameters()

@@ -159,6 +159,28 @@ int gsr_normal_fusion_pass(int64_t n, const int64_t* ids, const float* normals, 
 int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean_normals,
                            void* stream);
 
+/* ---- optimizer step after the path ----
+ * Fused multi-tensor Adam / AdamW: replaces `torch.optim.<optimizer_name>(param_groups, **args).step()` of
+ * gaustudio/pipelines/optimizers/base.py:19-30 (+ zero_grad, :32-34) for optimizer_name in {Adam, AdamW}
+ * (configs/vanilla.yaml:30-46: AdamW, eps 1e-15, one learning rate per Gaussian attribute) with ONE launch over
+ * all groups.  Per element: grad' = grad * grad_scale (1/world after a summing all-reduce);
+ *   decoupled != 0 (AdamW): p *= 1 - lr*weight_decay     else (Adam): grad' += weight_decay * p
+ *   m += (grad' - m)(1 - beta1);  v = v*beta2 + (1 - beta2) grad'^2;
+ *   p -= lr/(1 - beta1^step) * m / (sqrt(v)/sqrt(1 - beta2^step) + eps);   grad = 0 if zero_grad.
+ * `groups` is a HOST array of n_groups (<= GSR_ADAM_MAX_GROUPS) descriptors of DEVICE float tensors; step >= 1. */
+#define GSR_ADAM_MAX_GROUPS 16
+typedef struct gsr_adam_group {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  float lr;
+  float weight_decay;
+} gsr_adam_group;
+int gsr_adam_step(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, int64_t step,
+                  int decoupled, float grad_scale, int zero_grad, void* stream);
+
 /* Introspection for parity tests: copies internal state of the last forward out of the opaque buffers into
  * caller-provided DEVICE arrays (any may be NULL):
  *   point_list  uint32[R]   Gaussian index per sorted tile instance (== BinningState::point_list)
