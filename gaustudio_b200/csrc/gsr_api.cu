@@ -487,7 +487,7 @@ int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_wei
   return check(cudaGetLastError(), "normal_fusion_mean") ? 0 : -1;
 }
 
-int gsr_adam_step(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, int64_t step,
+int gsr_adam_step(int n_groups, const gsr_adam_group* groups, double beta1, double beta2, double eps, int64_t step,
                   int decoupled, float grad_scale, int zero_grad, void* stream) {
   if (n_groups <= 0) return 0;
   if (!groups || n_groups > GSR_ADAM_MAX_GROUPS) { g_err = "gsr_adam_step: 1..16 groups"; return -1; }

@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam(const __grid_constant__ A
   }
 }
 
-int launch_adam(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, long long step,
+int launch_adam(int n_groups, const gsr_adam_group* groups, double beta1, double beta2, double eps, long long step,
                 int decoupled, float grad_scale, int zero_grad, cudaStream_t st) {
   AdamTable t;
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
   unsigned blocks = 0;
   int k = 0;
   for (int i = 0; i < n_groups; i++) {
@@ -268,7 +268,7 @@ int launch_adam(int n_groups, const gsr_adam_group* groups, float beta1, float b
   t.first_block[k] = blocks;
   t.groups = k;
   if (!k) return 0;
-  k_adam<<<blocks, ADAM_THREADS, 0, st>>>(t, 1.0f - beta1, beta2, 1.0f - beta2, (float)(1.0 / std::sqrt(bc2)), eps, grad_scale,
+  k_adam<<<blocks, ADAM_THREADS, 0, st>>>(t, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)(1.0 / std::sqrt(bc2)), (float)eps, grad_scale,
                                           decoupled, zero_grad);
   return 0;
 }

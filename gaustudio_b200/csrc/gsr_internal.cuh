@@ -181,7 +181,7 @@ void launch_fusion_mean(int P, const float* sum_normals, const float* sum_weight
 }  // namespace gsr
 struct gsr_adam_group;
 namespace gsr {
-int launch_adam(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, long long step,
+int launch_adam(int n_groups, const gsr_adam_group* groups, double beta1, double beta2, double eps, long long step,
                 int decoupled, float grad_scale, int zero_grad, cudaStream_t st);
 
 }  // namespace gsr

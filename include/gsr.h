@@ -167,6 +167,7 @@ int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_wei
  *   decoupled != 0 (AdamW): p *= 1 - lr*weight_decay     else (Adam): grad' += weight_decay * p
  *   m += (grad' - m)(1 - beta1);  v = v*beta2 + (1 - beta2) grad'^2;
  *   p -= lr/(1 - beta1^step) * m / (sqrt(v)/sqrt(1 - beta2^step) + eps);   grad = 0 if zero_grad.
+ * beta1 / beta2 / eps are doubles like torch's Python scalars (1 - beta2 must not be formed in float: 1.3e-5 off).
  * `groups` is a HOST array of n_groups (<= GSR_ADAM_MAX_GROUPS) descriptors of DEVICE float tensors; step >= 1. */
 #define GSR_ADAM_MAX_GROUPS 16
 typedef struct gsr_adam_group {
@@ -178,7 +179,7 @@ typedef struct gsr_adam_group {
   float lr;
   float weight_decay;
 } gsr_adam_group;
-int gsr_adam_step(int n_groups, const gsr_adam_group* groups, float beta1, float beta2, float eps, int64_t step,
+int gsr_adam_step(int n_groups, const gsr_adam_group* groups, double beta1, double beta2, double eps, int64_t step,
                   int decoupled, float grad_scale, int zero_grad, void* stream);
 
 /* Introspection for parity tests: copies internal state of the last forward out of the opaque buffers into
