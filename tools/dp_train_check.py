@@ -41,6 +41,22 @@ if world > 1:
         ts = [torch.empty_like(t) for _ in range(world)]; dist.all_gather(ts, t)
         same.append(all(torch.equal(ts[0], x) for x in ts))
     res["identical_across_ranks"] = all(same)
+# size of the real thing: 59 floats per Gaussian at P = 1e6 (all six attribute tensors), one bucket, one all_reduce
+from gaustudio_b200.optimizers import FusedAdam
+big = torch.nn.Parameter(torch.randn(59_000_000, device=dev)); bb = parallel.GradBucket([big]); bb.flat.normal_()
+fa = FusedAdam([big], lr=1e-3, eps=1e-15)
+def timed(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); a, b = torch.cuda.Event(True), torch.cuda.Event(True); a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n
+res["adam_step_59M_ms"] = round(timed(lambda: fa.step(grad_scale=bb.grad_scale, zero_grad=False)), 4)
+res["adam_step_59M_GBps"] = round(59e6 * 28 / res["adam_step_59M_ms"] / 1e6, 1)
+if world > 1:
+    ms = timed(lambda: (bb.all_reduce(async_op=True), bb.wait()))
+    res["allreduce_59M_floats_ms"] = round(parallel.barrier_max_ms(ms, dev), 4)
+    res["allreduce_busbw_GBps"] = round(59e6 * 4 * 2 * (world - 1) / world / res["allreduce_59M_floats_ms"] / 1e6, 1)
+del big, bb, fa
 if rank == 0:
     solo, _, _ = run(lambda s: [(s * world + k) % 8 for k in range(world)], False)
     res["max_abs_diff_vs_single_process"] = max(float((a - b).abs().max()) for a, b in zip(dp, solo))
