@@ -69,6 +69,7 @@ class FusedAdam:
             g["params"] = [ps] if isinstance(ps, torch.Tensor) else list(ps)
             for k, v in self.defaults.items():
                 g.setdefault(k, v)
+            g["betas"] = tuple(g["betas"])
             self.param_groups.append(g)
         betas_eps = {(g["betas"], g["eps"]) for g in self.param_groups}
         if len(betas_eps) > 1:
@@ -119,6 +120,40 @@ class FusedAdam:
                                      int(self.decoupled), float(grad_scale), int(bool(zero_grad)), stream)
                 if rc < 0:
                     raise RuntimeError("gsr_adam_step failed: " + _lib.last_error())
+
+    def state_dict(self):
+        """torch.optim layout: parameters are numbered in group order; state holds step / exp_avg / exp_avg_sq."""
+        index = {id(p): i for i, (_, p) in enumerate(self._tensors())}
+        groups = []
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = [index[id(p)] for p in g["params"]]
+            groups.append(d)
+        state = {index[id(p)]: {"step": self.step_count, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}
+                 for p, st in self.state.items()}
+        return {"state": state, "param_groups": groups, "decoupled": self.decoupled}
+
+    def load_state_dict(self, sd):
+        """Resume: moments are copied onto the current parameters' devices; hyper-parameters come from the checkpoint."""
+        params = [p for _, p in self._tensors()]
+        if [len(g["params"]) for g in sd["param_groups"]] != [len(g["params"]) for g in self.param_groups]:
+            raise ValueError("FusedAdam.load_state_dict: parameter groups do not match")
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: v for k, v in saved.items() if k != "params"})
+            g["betas"] = tuple(g["betas"])
+        self.state = {}
+        steps = set()
+        for i, st in sd["state"].items():
+            p = params[int(i)]
+            if st["exp_avg"].shape != p.shape:
+                raise ValueError("FusedAdam.load_state_dict: moment shape does not match its parameter")
+            self.state[p] = {"exp_avg": st["exp_avg"].detach().to(device=p.device, dtype=torch.float32).contiguous().clone(),
+                             "exp_avg_sq": st["exp_avg_sq"].detach().to(device=p.device, dtype=torch.float32).contiguous().clone()}
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam.load_state_dict: one step count for all parameters (they move in one launch)")
+        self.step_count = steps.pop() if steps else 0
+        self.decoupled = bool(sd.get("decoupled", self.decoupled))
 
     def zero_grad(self, set_to_none=False):
         """Keeps the gradient tensors by default (the flat all-reduce bucket of parallel.GradBucket aliases them)."""

@@ -91,3 +91,26 @@ def test_bucket_all_reduce_world2():
         assert torch.equal(ga, torch.full((6, 3), 3.0))          # 1 + 2, summed over the ranks
         assert torch.allclose(gb, 6.0 * b)                        # (1 + 2) * 2 b
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+
+
+def test_fused_adam_state_dict_roundtrip():
+    """Checkpoint / resume of the optimizer state (host-side bookkeeping only; the step kernel needs a GPU)."""
+    from gaustudio_b200.optimizers import FusedAdam
+    a = torch.nn.Parameter(torch.randn(4, 3)); b = torch.nn.Parameter(torch.randn(5))
+    opt = FusedAdam([{"params": [a], "lr": 0.1}, {"params": [b], "lr": 0.2, "betas": [0.9, 0.999]}], eps=1e-15)
+    assert opt.param_groups[1]["betas"] == (0.9, 0.999)
+    opt.state[a] = {"exp_avg": torch.ones(4, 3), "exp_avg_sq": torch.full((4, 3), 2.0)}
+    opt.state[b] = {"exp_avg": torch.zeros(5), "exp_avg_sq": torch.zeros(5)}
+    opt.step_count = 7
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["params"] == [0] and sd["param_groups"][1]["params"] == [1] and sd["state"][0]["step"] == 7
+    a2 = torch.nn.Parameter(torch.randn(4, 3)); b2 = torch.nn.Parameter(torch.randn(5))
+    new = FusedAdam([{"params": [a2], "lr": 1.0}, {"params": [b2], "lr": 1.0}])
+    new.load_state_dict(sd)
+    assert new.step_count == 7 and new.param_groups[0]["lr"] == 0.1 and new.param_groups[1]["lr"] == 0.2
+    assert new.param_groups[0]["eps"] == 1e-15 and torch.equal(new.state[a2]["exp_avg_sq"], torch.full((4, 3), 2.0))
+    assert new.state[a2]["exp_avg"].data_ptr() != opt.state[a]["exp_avg"].data_ptr()
+    with pytest.raises(ValueError):
+        FusedAdam([a2]).load_state_dict(sd)
+    with pytest.raises(ValueError):
+        FusedAdam([{"params": [a]}, {"params": [b], "eps": 1e-8}], eps=1e-15)  # one launch: one eps
