@@ -17,27 +17,26 @@ from torch import nn
 
 from . import _lib
 
-optimizers = {}
+optimizers = {}  # name -> class (public, like the reference's module-level dict)
 
 
 def register(name):
-    def decorator(cls):
+    def _add(cls):
         optimizers[name] = cls
         return cls
-    return decorator
+    return _add
 
 
 def make(config):
-    if isinstance(config, str):
-        name = config
-        config = {}
-    else:
-        name = config.get("name")
+    """`config`: a registered name, or a mapping with `name` (the mapping itself is handed to the constructor)."""
+    name, options = (config, {}) if isinstance(config, str) else (config.get("name"), config)
     if not name:
         raise ValueError("Optimizer name is required")
-    if name not in optimizers:
-        raise ValueError(f"Unknown optimizer: {name}")
-    return optimizers[name](config)
+    try:
+        cls = optimizers[name]
+    except KeyError:
+        raise ValueError(f"Unknown optimizer: {name}") from None
+    return cls(options)
 
 
 class _AdamGroup(C.Structure):  # gsr_adam_group, include/gsr.h
@@ -198,12 +197,13 @@ class GeneralOptimizer(BaseOptimizer):
     attribute `_<name>` becomes an nn.Parameter), else every model parameter in one group."""
 
     def _initialize_internal_state(self):
-        if "params" in self.config:
-            self.param_groups = []
-            for name, args in self.config["params"].items():
-                parameter = nn.Parameter(getattr(self.model, "_" + name))
-                parameter.requires_grad = True
-                setattr(self.model, "_" + name, parameter)
-                self.param_groups.append({"params": getattr(self.model, "_" + name), "name": name, **(args or {})})
-        else:
+        spec = self.config.get("params") if hasattr(self.config, "get") else None
+        if spec is None:
             self.param_groups = self.model.parameters()
+            return
+        self.param_groups = []
+        for name, options in spec.items():
+            attr = "_" + name
+            leaf = nn.Parameter(getattr(self.model, attr), requires_grad=True)
+            setattr(self.model, attr, leaf)
+            self.param_groups.append(dict(options or {}, params=leaf, name=name))
