@@ -99,6 +99,37 @@ def export_ply(model, path):
         f.write(data.tobytes())
 
 
+def export_points_ply(path, xyz, rgb=None, normals=None):
+    """Surface point cloud (the `fused.ply` of gaustudio/scripts/extract_pcd.py:339-352, written there through
+    open3d's `write_point_cloud`): binary little-endian, double x y z [nx ny nz] + uchar red green blue, the property
+    layout open3d emits.  Tensors or arrays; colours in [0, 1]."""
+    def host(a):
+        return None if a is None else np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)
+    xyz, rgb, normals = host(xyz), host(rgb), host(normals)
+    n = xyz.shape[0]
+    fields = [("x", "<f8"), ("y", "<f8"), ("z", "<f8")]
+    if normals is not None:
+        fields += [("nx", "<f8"), ("ny", "<f8"), ("nz", "<f8")]
+    if rgb is not None:
+        fields += [("red", "u1"), ("green", "u1"), ("blue", "u1")]
+    rec = np.empty(n, dtype=fields)
+    for i, k in enumerate("xyz"):
+        rec[k] = xyz[:, i]
+    if normals is not None:
+        for i, k in enumerate(("nx", "ny", "nz")):
+            rec[k] = normals[:, i]
+    if rgb is not None:
+        c = np.clip(np.nan_to_num(rgb.astype(np.float64)) * 255.0, 0, 255).astype(np.uint8)  # open3d truncates
+        for i, k in enumerate(("red", "green", "blue")):
+            rec[k] = c[:, i]
+    names = {"<f8": "double", "u1": "uchar"}
+    head = ["ply", "format binary_little_endian 1.0", f"element vertex {n}"] + \
+           [f"property {names[t]} {k}" for k, t in fields] + ["end_header"]
+    with open(path, "wb") as f:
+        f.write(("\n".join(head) + "\n").encode("ascii"))
+        f.write(rec.tobytes())
+
+
 def camera_from_json(entry):
     """One `cameras.json` entry (id, img_name, width, height, position, rotation (camera-to-world), fx, fy)."""
     c2w = np.eye(4)

@@ -66,3 +66,20 @@ def test_cameras_json_matches_look_at(tmp_path):
     assert np.allclose(back.world_view_transform.numpy(), cam.world_view_transform.numpy(), atol=1e-5)
     assert np.allclose(back.full_proj_transform.numpy(), cam.full_proj_transform.numpy(), atol=1e-5)
     assert abs(back.FoVx - cam.FoVx) < 1e-9 and (back.image_width, back.image_height) == (320, 240)
+
+
+def test_surface_point_cloud_ply(tmp_path):
+    g = np.random.default_rng(3)
+    xyz = g.normal(size=(50, 3)).astype(np.float32); rgb = g.random((50, 3)).astype(np.float32)
+    nrm = g.normal(size=(50, 3)).astype(np.float32); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    p = tmp_path / "fused.ply"
+    io.export_points_ply(str(p), torch.from_numpy(xyz), torch.from_numpy(rgb), nrm)
+    head = p.read_bytes().split(b"end_header\n")[0].decode().splitlines()
+    assert head[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 50"]
+    assert [l.split()[1:] for l in head[3:]] == [["double", k] for k in ("x", "y", "z", "nx", "ny", "nz")] + \
+        [["uchar", k] for k in ("red", "green", "blue")]
+    v = io.read_ply_vertices(str(p))
+    assert np.allclose(np.stack([v["x"], v["y"], v["z"]], 1), xyz) and np.allclose(np.stack([v["nx"], v["ny"], v["nz"]], 1), nrm)
+    assert np.array_equal(np.stack([v["red"], v["green"], v["blue"]], 1), (rgb.astype(np.float64) * 255).astype(np.uint8))
+    io.export_points_ply(str(p), xyz)  # positions only
+    assert io.read_ply_vertices(str(p)).dtype.names == ("x", "y", "z")
