@@ -129,7 +129,8 @@ int gsr_depth2point(const float* depth, int width, int height, float fx, float f
  *               on out_mask pixels (min/max over them, masked-out pixels entering the filter as 0, disc support of
  *               radius d/2, centre weight 1, REFLECT_101 border), the input depth elsewhere.
  * depth/out_depth: device float[H*W]; mask/out_mask: device uint8[H*W] (torch.bool layout); d odd, 1..15;
- * scratch: 2 device words owned by the caller (the depth range never visits the host). */
+ * scratch: 2 device words owned by the caller (the depth range never visits the host).
+ * Reference quirk kept: max == min (constant depth, one surviving pixel) divides 0 by 0 and yields NaN there too. */
 int gsr_masked_bilateral(const float* depth, const unsigned char* mask, int width, int height, int d,
                          float sigma_color, float sigma_space, float* out_depth, unsigned char* out_mask,
                          unsigned int* scratch, void* stream);
