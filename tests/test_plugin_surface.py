@@ -72,3 +72,29 @@ def test_vanilla_yaml_keys_accepted():
     r = renderers.make({"name": "vanilla_renderer", "scaling_modifier": 1., "white_background": False,
                         "convert_SHs_python": False, "compute_cov3D_python": False, "debug": False})
     assert r.debug is False
+
+
+def test_extract_surface_fails_loudly_without_cuda():
+    """The post-pass mirrors extract_pcd.py's function names / arguments and has no CPU path."""
+    import inspect
+    import math
+    import types
+
+    import pytest
+    import torch
+
+    from gaustudio_b200 import extract
+    from gaustudio_b200.camera import orbit_cameras
+    assert list(inspect.signature(extract.masked_bilateral_filter).parameters) == \
+        ["depth_map", "mask", "d", "sigma_color", "sigma_space"]                      # extract_pcd.py:185
+    assert list(inspect.signature(extract.normal_fusion).parameters)[:5] == \
+        ["pcd", "all_ids_list", "all_normals_list", "all_confidences_list", "cameras"]  # extract_pcd.py:108
+    sig = inspect.signature(extract.masked_bilateral_filter).parameters
+    assert (sig["d"].default, sig["sigma_color"].default, sig["sigma_space"].default) == (3, 75, 75)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        extract.masked_bilateral_filter(torch.rand(8, 8), torch.ones(8, 8, dtype=torch.bool))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        extract.normal_fusion(types.SimpleNamespace(_xyz=torch.rand(4, 3)), [], [], [], [])
+    cams = orbit_cameras(6, 3.0, 30.0, 64, 48, 0.8, 0.6)
+    norm = extract.getNerfppNorm(cams)   # datasets/utils.py:82-104: radius = 1.1 * max distance to the mean centre
+    assert abs(norm["radius"] - 1.1 * 3.0 * math.cos(math.radians(30.0))) < 1e-6 and norm["translate"].shape == (3,)
