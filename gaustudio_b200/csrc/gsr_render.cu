@@ -21,6 +21,7 @@
 //    accumulator, instead of 11-12 atomicAdd per (pixel, Gaussian) pair (backward.cu:559-607); traversal
 //    starts at the tile's largest n_contrib instead of the end of the list.
 #include "gsr_internal.cuh"
+#include <cstdlib>
 
 namespace gsr {
 
@@ -151,6 +152,10 @@ __device__ __forceinline__ void ring_init(Ring& r) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// HALF (experimental, GSR_HALFWARP=1; NOT yet validated on a GPU -- see DESIGN.md 7b.1): every consumer warp owns two 4x4
+// blocks instead of one 8x4 block; each half-warp walks its own survivor mask, so one loop iteration composites two
+// different Gaussians and the 16-px-wide cull removes pairs the 8x4 rectangle keeps.  Per-pixel order is unchanged.
+template <bool HALF>
 __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
                                                                const float4* __restrict__ splat,
                                                                float* __restrict__ out_color,
@@ -192,11 +197,13 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
 
   // ---------------- consumers: warp w owns the 8x4 sub-tile at (w&1, w>>1) ----------------
   const int sx0 = tx * TILE_X + (warp & 1) * 8, sy0 = ty * TILE_Y + (warp >> 1) * 4;
-  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+  const int px = HALF ? sx0 + 4 * (lane >> 4) + (lane & 3) : sx0 + (lane & 7);
+  const int py = HALF ? sy0 + ((lane >> 2) & 3) : sy0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
   const float rx0 = (float)sx0, ry0 = (float)sy0;
-  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const float rx1 = (float)min(sx0 + (HALF ? 3 : 7), W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const float rbx0 = (float)(sx0 + 4), rbx1 = (float)min(sx0 + 7, W - 1);  // HALF: the right-hand 4x4 block
 
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
@@ -226,10 +233,25 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
       bool keep = false;
       if (j < cnt) keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
       unsigned mask = __ballot_sync(FULL, keep);
-      while (mask) {
-        const int jj = base + __ffs(mask) - 1;
-        mask &= mask - 1;
-        if (done) continue;
+      unsigned maskB = 0;
+      if constexpr (HALF) {
+        bool keepB = false;
+        if (j < cnt && rbx0 <= rbx1) keepB = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rbx0, ry0, rbx1, ry1);
+        maskB = __ballot_sync(FULL, keepB);
+      }
+      while (HALF ? (mask | maskB) : mask) {
+        int jj;
+        if constexpr (HALF) {
+          const unsigned mine = (lane & 16) ? maskB : mask;  // each half-warp pops its own next survivor
+          jj = base + __ffs(mine) - 1;
+          mask &= mask - 1;
+          maskB &= maskB - 1;
+          if (mine == 0 || done) continue;
+        } else {
+          jj = base + __ffs(mask) - 1;
+          mask &= mask - 1;
+          if (done) continue;
+        }
         const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
         // forward.cu:343-356 with the contraction of the reference SASS
         const float dx = q0.x - pxf, dy = q0.y - pyf;
@@ -293,6 +315,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
+template <bool HALF>
 __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int gx, const float* __restrict__ bg,
                                                                ImageView im, BinView bin,
                                                                const float4* __restrict__ splat,
@@ -328,11 +351,13 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
   }
 
   const int sx0 = tx * TILE_X + (warp & 1) * 8, sy0 = ty * TILE_Y + (warp >> 1) * 4;
-  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+  const int px = HALF ? sx0 + 4 * (lane >> 4) + (lane & 3) : sx0 + (lane & 7);
+  const int py = HALF ? sy0 + ((lane >> 2) & 3) : sy0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
   const float rx0 = (float)sx0, ry0 = (float)sy0;
-  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const float rx1 = (float)min(sx0 + (HALF ? 3 : 7), W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const float rbx0 = (float)(sx0 + 4), rbx1 = (float)min(sx0 + 7, W - 1);  // HALF: the right-hand 4x4 block
   const size_t pid = (size_t)py * W + px, HW = (size_t)W * H;
 
   const float T_final = inside ? im.final_T[pid] : 0.f;
@@ -351,9 +376,14 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
   float acc_d = 0.f, last_d = 0.f, acc_o = 0.f, last_o = 0.f, last_alpha = 0.f;
   const int warp_max = (int)__reduce_max_sync(FULL, (unsigned)last_contributor);
-  // which lane publishes which reduced component (see the butterfly below)
-  const bool pub = ((lane & 3) == 0) || lane == 1 || lane == 17;
-  const int slot = ((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9);
+  // HALF: traversal bounds of the two 4x4 blocks (a block whose pixels all stopped early skips the tail entries)
+  const int maxA = HALF ? (int)__reduce_max_sync(FULL, (lane & 16) ? 0u : (unsigned)last_contributor) : 0;
+  const int maxB = HALF ? (int)__reduce_max_sync(FULL, (lane & 16) ? (unsigned)last_contributor : 0u) : 0;
+  // which lane publishes which reduced component (see the butterflies below)
+  const bool pub = HALF ? (((lane & 1) == 0) || (lane & 7) == 1) : (((lane & 3) == 0) || lane == 1 || lane == 17);
+  const int slot = HALF ? (((lane & 1) == 0) ? ((lane & 8) ? 5 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0)
+                                             : ((lane & 8) ? 9 : 4))
+                        : (((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9));
 
   for (int b = 0; b < nb; b++) {
     const int s = b % NSTAGE;
@@ -364,11 +394,29 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
       for (int base = 0; base < cnt; base += 32) {
         const int j = cnt - 1 - (base + lane);  // lane 0 = farthest entry of this chunk
         bool keep = false;
-        if (j >= 0 && lo + j < warp_max) keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
+        if (j >= 0 && lo + j < (HALF ? maxA : warp_max))
+          keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
         unsigned mask = __ballot_sync(FULL, keep);
-        while (mask) {
-          const int jj = cnt - 1 - (base + __ffs(mask) - 1);
-          mask &= mask - 1;
+        unsigned maskB = 0;
+        if constexpr (HALF) {
+          bool keepB = false;
+          if (j >= 0 && lo + j < maxB && rbx0 <= rbx1)
+            keepB = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rbx0, ry0, rbx1, ry1);
+          maskB = __ballot_sync(FULL, keepB);
+        }
+        while (HALF ? (mask | maskB) : mask) {
+          int jj;
+          bool has = true;
+          if constexpr (HALF) {
+            const unsigned mine = (lane & 16) ? maskB : mask;  // each half-warp pops its own next survivor
+            has = mine != 0;
+            jj = has ? cnt - 1 - (base + __ffs(mine) - 1) : 0;
+            mask &= mask - 1;
+            maskB &= maskB - 1;
+          } else {
+            jj = cnt - 1 - (base + __ffs(mask) - 1);
+            mask &= mask - 1;
+          }
           const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
           const float dx = q0.x - pxf, dy = q0.y - pyf;
           const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
@@ -378,8 +426,14 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
           const float G = expf(power);
           const float alpha = fminf(0.99f, q1.y * G);
           // backward.cu:520-537: entries at or beyond n_contrib, power > 0 and alpha < 1/255 are skipped
-          const bool valid = (lo + jj < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-          if (!__any_sync(FULL, valid)) continue;
+          const bool valid = has && (lo + jj < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+          unsigned vb = 0;  // HALF: which half-warps have a contributing pixel
+          if constexpr (HALF) {
+            vb = __ballot_sync(FULL, valid);
+            if (!vb) continue;
+          } else {
+            if (!__any_sync(FULL, valid)) continue;
+          }
           const float4 q2 = sb[jj * SPLAT_F4 + 2];
           float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
           if (valid) {
@@ -416,29 +470,53 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
             v9 = h * gdy * dy;
             v4 += G * dL_dalpha;
           }
-          // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
-          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-          float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
-          a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
-          a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
-          a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
-          a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
-          float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
-          b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
-          b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
-          float c = h4 ? b1 : b0;
-          c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
-          c += __shfl_xor_sync(FULL, c, 2);
-          c += __shfl_xor_sync(FULL, c, 1);
-          // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
-          float e = h16 ? v9 : v8;
-          e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
-          e += __shfl_xor_sync(FULL, e, 8);
-          e += __shfl_xor_sync(FULL, e, 4);
-          e += __shfl_xor_sync(FULL, e, 2);
-          e += __shfl_xor_sync(FULL, e, 1);
-          // accumulator slots: 0-2 colour, 3 depth, 4 opacity, 5-6 mean2D, 7-9 conic (xx, xy, yy)
-          if (pub) atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 3) == 0) ? c : e);
+          if constexpr (HALF) {
+            // 16-lane transposed butterfly per half-warp (12 shuffles): lane bits 8/4/2 pick the component,
+            // comp = (bit8 ? 5 : 0) + (bit4 ? 2 : 0) + (bit2 ? 1 : 0) in `c`; components 4 / 9 (by bit8) in `e`
+            const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+            float a0 = h8 ? v5 : v0, a1 = h8 ? v6 : v1, a2 = h8 ? v7 : v2, a3 = h8 ? v8 : v3, a4 = h8 ? v9 : v4;
+            a0 += __shfl_xor_sync(FULL, h8 ? v0 : v5, 8);
+            a1 += __shfl_xor_sync(FULL, h8 ? v1 : v6, 8);
+            a2 += __shfl_xor_sync(FULL, h8 ? v2 : v7, 8);
+            a3 += __shfl_xor_sync(FULL, h8 ? v3 : v8, 8);
+            a4 += __shfl_xor_sync(FULL, h8 ? v4 : v9, 8);
+            float b0 = h4 ? a2 : a0, b1 = h4 ? a3 : a1;
+            b0 += __shfl_xor_sync(FULL, h4 ? a0 : a2, 4);
+            b1 += __shfl_xor_sync(FULL, h4 ? a1 : a3, 4);
+            float e = a4 + __shfl_xor_sync(FULL, a4, 4);
+            float c = h2 ? b1 : b0;
+            c += __shfl_xor_sync(FULL, h2 ? b0 : b1, 2);
+            c += __shfl_xor_sync(FULL, c, 1);
+            e += __shfl_xor_sync(FULL, e, 2);
+            e += __shfl_xor_sync(FULL, e, 1);
+            // each half-warp publishes to its own Gaussian (q2.z differs between the halves)
+            if (pub && (vb & ((lane & 16) ? 0xffff0000u : 0x0000ffffu)))
+              atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 1) == 0) ? c : e);
+          } else {
+            // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
+            a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
+            a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
+            a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
+            a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
+            float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
+            b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
+            b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
+            float c = h4 ? b1 : b0;
+            c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
+            c += __shfl_xor_sync(FULL, c, 2);
+            c += __shfl_xor_sync(FULL, c, 1);
+            // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
+            float e = h16 ? v9 : v8;
+            e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
+            e += __shfl_xor_sync(FULL, e, 8);
+            e += __shfl_xor_sync(FULL, e, 4);
+            e += __shfl_xor_sync(FULL, e, 2);
+            e += __shfl_xor_sync(FULL, e, 1);
+            // accumulator slots: 0-2 colour, 3 depth, 4 opacity, 5-6 mean2D, 7-9 conic (xx, xy, yy)
+            if (pub) atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 3) == 0) ? c : e);
+          }
         }
       }
     }
@@ -449,10 +527,20 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
 
 }  // namespace
 
+// Experimental half-warp compositing: opt-in with GSR_HALFWARP=1, read once per process.
+static bool halfwarp_enabled() {
+  static const bool on = [] { const char* e = getenv("GSR_HALFWARP"); return e && e[0] == '1'; }();
+  return on;
+}
+
 void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, float* out_color,
                        float* out_depth, float* out_median, float* out_opacity, cudaStream_t st) {
-  k_render_fwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median,
-                                                  out_opacity);
+  if (halfwarp_enabled())
+    k_render_fwd<true><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median,
+                                                           out_opacity);
+  else
+    k_render_fwd<false><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median,
+                                                            out_opacity);
 }
 
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
@@ -460,8 +548,12 @@ void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView 
                        const float* dL_dopacity, cudaStream_t st) {
   // d(pixel coordinate)/d(ndc): backward.cu:493-494 (double-precision product rounded to float)
   const float ddelx_dx = (float)(0.5 * W), ddely_dy = (float)(0.5 * H);
-  k_render_bwd<<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
-                                                  dL_dmedian, dL_dopacity, ddelx_dx, ddely_dy);
+  if (halfwarp_enabled())
+    k_render_bwd<true><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
+                                                           dL_dmedian, dL_dopacity, ddelx_dx, ddely_dy);
+  else
+    k_render_bwd<false><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
+                                                            dL_dmedian, dL_dopacity, ddelx_dx, ddely_dy);
 }
 
 }  // namespace gsr
