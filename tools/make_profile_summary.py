@@ -41,7 +41,13 @@ open(os.path.join(out, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "
 grp = {"preprocess_fwd": traffic.get("k_preprocess_fwd"), "render_fwd": traffic.get("k_render_fwd"), "render_bwd": traffic.get("k_render_bwd"),
        "preprocess_bwd": traffic.get("k_preprocess_bwd"),
        "binning": sum(v for k, v in traffic.items() if k in ("k_tile_scan", "k_scatter", "k_tile_sort")) or None}
-json.dump({k: v for k, v in grp.items() if v}, open(os.path.join(out, "ncu_traffic.json"), "w"), indent=1)
+# merge into the committed file (bench.py reads it) only when the capture holds all five stages of a view;
+# a partial capture (e.g. tools/profile_aux.py) must not drop the stages it did not see
+tf = os.path.join(out, "ncu_traffic.json")
+if all(grp.values()):
+    old = json.load(open(tf)) if os.path.exists(tf) else {}
+    old.update(grp)
+    json.dump(old, open(tf, "w"), indent=1)
 if launches:
     rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
     tot = {}; n = {}
