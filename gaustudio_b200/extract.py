@@ -145,12 +145,13 @@ def normal_fusion(pcd, all_ids_list, all_normals_list, all_confidences_list, cam
     mean = _fusion_pass(xyz, all_ids_list, all_normals_list, all_confidences_list, cam_ts, mean, sums, weights, None)
     unique_ids = torch.nonzero(touched, as_tuple=False).flatten()
     mean = mean[unique_ids]
-    if not smooth:
+    if not smooth or unique_ids.numel() == 0:
         return unique_ids, mean
     # spatial smoothing over the 10 nearest surface points (extract_pcd.py:170-181); neighbour search on the host
     from scipy.spatial import cKDTree
     pts = xyz[unique_ids].cpu().numpy()
-    dist, idx = cKDTree(pts).query(pts, k=10)
+    dist, idx = cKDTree(pts).query(pts, k=min(10, len(pts)))  # (the reference needs >= 10 surface points)
+    dist, idx = dist.reshape(len(pts), -1), idx.reshape(len(pts), -1)
     w = torch.exp(-torch.from_numpy(dist).to(dev) / 0.1)
     sm = (mean[torch.from_numpy(idx).to(dev)].double() * w.unsqueeze(-1)).sum(1).float()
     return unique_ids, torch.nn.functional.normalize(sm, p=2, dim=1)
