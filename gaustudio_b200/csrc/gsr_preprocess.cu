@@ -332,9 +332,11 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
           tiles = (uint32_t)((y1 - y0) * (x1 - x0));
           g.clamped[idx] = cl;
           float4* s = g.splat + (size_t)idx * SPLAT_F4;
+          const float opac = a.fused ? act_sigmoid(a.opacities[idx]) : a.opacities[idx];
+          // tau = 2 ln(255 o): alpha >= 1/255 needs the conic form <= tau (block cull of the compositing kernels)
           s[0] = make_float4(px, py, conA, conB);
-          s[1] = make_float4(conC, a.fused ? act_sigmoid(a.opacities[idx]) : a.opacities[idx], p_view.z, rgb[0]);
-          s[2] = make_float4(rgb[1], rgb[2], __int_as_float(idx), __int_as_float(radius_i));
+          s[1] = make_float4(conC, opac, p_view.z, rgb[0]);
+          s[2] = make_float4(rgb[1], rgb[2], __int_as_float(idx), 2.f * logf(255.f * opac));
         }
       }
     }
@@ -387,10 +389,20 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
   float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
   if (vis) { g0 = ga[0]; g1 = ga[1]; g2 = ga[2]; }
   // accumulator layout (written by the render backward): g0 = {dcol.r, dcol.g, dcol.b, ddepth},
-  // g1 = {dopacity, dmean2D.x, dmean2D.y, dconic.xx}, g2 = {dconic.xy, dconic.yy, -, -}
+  // g1 = {dopacity, sum u dx, sum u dy, sum u dx^2}, g2 = {sum u dx dy, sum u dy^2, -, -} with u = dL/dG * G per
+  // (pixel, Gaussian) pair and d = mean2D - pixel.  G = exp(-(A dx^2 + C dy^2)/2 - B dx dy) gives
+  //   dL/dmean2D = -(A Sx + B Sy, C Sy + B Sx) * (W/2, H/2)      (backward.cu:493-494, 598-599; quirk 6)
+  //   dL/dconic  = -1/2 (Sxx, Sxy, Syy)                           (backward.cu:602-604)
   const float dL_dcolor[3] = {g0.x, g0.y, g0.z};
-  const float dL_ddepth = g0.w, dL_dopac = g1.x, dm2x = g1.y, dm2y = g1.z;
-  const float dcon_x = g1.w, dcon_y = g2.x, dcon_w = g2.y;
+  const float dL_ddepth = g0.w, dL_dopac = g1.x;
+  float dm2x = 0.f, dm2y = 0.f;
+  if (vis) {
+    const float4 s0 = g.splat[(size_t)idx * SPLAT_F4], s1 = g.splat[(size_t)idx * SPLAT_F4 + 1];
+    const float cA = s0.z, cB = s0.w, cC = s1.x;
+    dm2x = -(cA * g1.y + cB * g1.z) * (float)(0.5 * a.W);
+    dm2y = -(cC * g1.z + cB * g1.y) * (float)(0.5 * a.H);
+  }
+  const float dcon_x = -0.5f * g1.w, dcon_y = -0.5f * g2.x, dcon_w = -0.5f * g2.y;
 
   a.dL_dmean2D[3 * idx] = dm2x; a.dL_dmean2D[3 * idx + 1] = dm2y; a.dL_dmean2D[3 * idx + 2] = 0.f;
   if (a.fused) {

@@ -9,17 +9,25 @@
 // What is different (B200):
 //  * a dedicated producer warp walks the tile's sorted index list and stages the 48-byte splat records of
 //    the next batches into a shared-memory ring with asynchronous 16-byte copies (cp.async, completion on an
-//    mbarrier), NSTAGE batches ahead of the 8 consumer warps -- no CTA-wide barrier in the loop, and
+//    mbarrier), NSTAGE batches ahead of the consumer warps -- no CTA-wide barrier in the loop, and
 //    rgb/depth come from shared memory instead of per-pair global loads (forward.cu:365-366).  Only the
-//    part of the list a tile really consumes is ever gathered (early termination / n_contrib bound);
-//  * each warp owns an 8x4 pixel sub-tile and first tests every staged Gaussian against its sub-tile with a
-//    conservative bound on alpha (minimum of the conic form over the rectangle); only survivors are
-//    evaluated.  A pair is skipped only if the reference would `continue` past it for every pixel of the
-//    sub-tile (alpha < 1/255), so results are unchanged while most pair evaluations disappear;
-//  * backward: the 10 per-Gaussian gradient components are reduced across the warp with a transposed
-//    shuffle butterfly and issued as ONE predicated red.global per (warp, Gaussian) into a packed 48-byte
-//    accumulator, instead of 11-12 atomicAdd per (pixel, Gaussian) pair (backward.cu:559-607); traversal
-//    starts at the tile's largest n_contrib instead of the end of the list.
+//    part of the list a tile really consumes is ever gathered (early termination / n_contrib bound).  All
+//    waits are blocking mbarrier waits (no polling of shared flags): when every pixel of a tile is finished
+//    the producer completes the next, never-gathered batch with plain arrivals (a "poison" batch) and the
+//    parked consumer warps leave through it;
+//  * every 8x4 pixel block first tests the staged Gaussians against its rectangle with a conservative bound
+//    on alpha (minimum of the conic form over the rectangle, threshold 2 ln(255 o) precomputed per Gaussian);
+//    only survivors are evaluated.  A pair is skipped only if the reference would `continue` past it for
+//    every pixel of the block (alpha < 1/255), so results are unchanged while most evaluations disappear;
+//  * backward: one lane owns NSUB pixels (one in each of the warp's NSUB 8x4 blocks) and sums a Gaussian's
+//    gradient contributions over its own pixels in registers before the warp-level reduction, so the
+//    transposed shuffle butterfly + predicated red.global run once per (warp region, Gaussian) instead of
+//    once per (8x4 block, Gaussian) -- and instead of 11-12 atomicAdd per (pixel, Gaussian) pair
+//    (backward.cu:559-607).  The per-pair arithmetic is re-derived for instruction count (see bwd_pair):
+//    one scalar "behind" recurrence for all five blended channels, and the mean / conic gradients are
+//    accumulated as raw moments of u = dL/dG * G (sum u dx, u dy, u dx^2, u dx dy, u dy^2) that the
+//    per-Gaussian kernel turns into dL/dmean2D and dL/dconic.  Traversal starts at the tile's largest
+//    n_contrib instead of the end of the list.
 #include "gsr_internal.cuh"
 #include <cstdlib>
 
@@ -30,8 +38,7 @@ namespace {
 constexpr int RB = 128;                       // records per pipeline stage
 constexpr int NSTAGE = 4;                     // ring depth: consumer warps may drift this many batches apart
 constexpr int STAGE_F4 = RB * SPLAT_F4;       // float4 per stage (6 KB)
-constexpr int NCONS = TILE_PIX / 32;          // 8 consumer warps (one 8x4 sub-tile each) + 1 producer warp
-constexpr int RENDER_THREADS = TILE_PIX + 32;
+constexpr int NBLK = TILE_PIX / 32;           // 8 blocks of 8x4 pixels per tile
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -65,19 +72,6 @@ __device__ __forceinline__ void stage_gather(float4* dst, const float4* __restri
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned b = smem_u32(bar);
   asm volatile(
@@ -93,75 +87,90 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// Conservative sub-tile test.  Returns false only if alpha = min(0.99, o*exp(power)) < 1/255 for EVERY pixel
+// Conservative block test.  Returns false only if alpha = min(0.99, o*exp(power)) < 1/255 for EVERY pixel
 // centre in [rx0,rx1]x[ry0,ry1] (the reference skips such pairs, forward.cu:353-355 / backward.cu:535-537).
-// With q(d) = A dx^2 + 2B dx dy + C dy^2 = -2*power, alpha >= 1/255 needs q <= tau = 2 ln(255 o).  q is convex
-// (conic positive definite), so its minimum over the rectangle is 0 if the centre is inside, else it lies on
-// an edge facing the centre; each facing edge is a 1-D quadratic minimised in closed form.  The margin covers
-// the rounding of the per-pixel evaluation (relative 1e-5 of the largest term magnitude + 1e-3 absolute);
-// any non-finite / non-PD input keeps the pair.
-__device__ __forceinline__ bool may_touch(const float4 q0, const float4 q1, float rx0, float ry0, float rx1, float ry1) {
-  const float A = q0.z, B = q0.w, C = q1.x, o = q1.y;
-  if (o < 0.0039f) return false;  // alpha <= o < 1/255 everywhere (exp(power) <= 1)
-  const float dxlo = q0.x - rx1, dxhi = q0.x - rx0, dylo = q0.y - ry1, dyhi = q0.y - ry0;
+// With q(d) = A dx^2 + 2B dx dy + C dy^2 = -2*power, alpha >= 1/255 needs q <= tau = 2 ln(255 o) (stored in
+// the record by the projection kernel).  q is convex (conic positive definite), so its minimum over the
+// rectangle is 0 if the centre is inside, else it lies on an edge facing the centre; each facing edge is a
+// 1-D quadratic minimised in closed form.  The edge minimiser uses an approximate reciprocal: an error in the
+// minimiser's position only enters q to second order (and not at all when it is clamped to a corner).  The
+// margin covers the rounding of the per-pixel evaluation (relative 1e-5 of the largest term magnitude + 1e-3
+// absolute); any non-finite / non-PD / extreme input keeps the pair.
+struct CullRec {
+  float gx, gy, A, B, C, tau, nBiC, nBiA;  // nBiC = -B / C, nBiA = -B / A
+  bool live, odd;                          // live: opacity can reach 1/255 at all; odd: keep unconditionally
+};
+__device__ __forceinline__ CullRec cull_prep(const float4 q0, const float4 q1, const float tau) {
+  CullRec r;
+  r.gx = q0.x; r.gy = q0.y; r.A = q0.z; r.B = q0.w; r.C = q1.x; r.tau = tau;
+  r.live = !(q1.y < 0.0039f);  // alpha <= o < 1/255 everywhere (exp(power) <= 1)
+  r.odd = !(r.A > 1e-30f && r.C > 1e-30f && r.A * r.C - r.B * r.B > 0.f && r.A < 1e30f && r.C < 1e30f);
+  float iC, iA;  // A, C in (1e-30, 1e30) whenever the values are used: plain MUFU.RCP is safe
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iC) : "f"(r.C));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(r.A));
+  r.nBiC = -r.B * iC;
+  r.nBiA = -r.B * iA;
+  return r;
+}
+__device__ __forceinline__ bool may_touch(const CullRec& r, float rx0, float ry0, float rx1, float ry1) {
+  if (!r.live) return false;
+  const float dxlo = r.gx - rx1, dxhi = r.gx - rx0, dylo = r.gy - ry1, dyhi = r.gy - ry0;
   const bool inx = dxlo <= 0.f && dxhi >= 0.f, iny = dylo <= 0.f && dyhi >= 0.f;
-  if (inx && iny) return true;
-  if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true;
+  if ((inx && iny) || r.odd) return true;
   float qmin = 3.0e38f;
   if (!inx) {
     const float dxe = dxlo > 0.f ? dxlo : dxhi;
-    const float dys = fminf(fmaxf(-B * dxe / C, dylo), dyhi);
-    qmin = A * dxe * dxe + 2.f * B * dxe * dys + C * dys * dys;
+    const float dys = fminf(fmaxf(r.nBiC * dxe, dylo), dyhi);
+    qmin = r.A * dxe * dxe + 2.f * r.B * dxe * dys + r.C * dys * dys;
   }
   if (!iny) {
     const float dye = dylo > 0.f ? dylo : dyhi;
-    const float dxs = fminf(fmaxf(-B * dye / A, dxlo), dxhi);
-    qmin = fminf(qmin, A * dxs * dxs + 2.f * B * dxs * dye + C * dye * dye);
+    const float dxs = fminf(fmaxf(r.nBiA * dye, dxlo), dxhi);
+    qmin = fminf(qmin, r.A * dxs * dxs + 2.f * r.B * dxs * dye + r.C * dye * dye);
   }
   const float mx = fmaxf(fabsf(dxlo), fabsf(dxhi)), my = fmaxf(fabsf(dylo), fabsf(dyhi));
-  const float S = A * mx * mx + C * my * my + 2.f * fabsf(B) * mx * my;
-  const float tau = 2.f * logf(255.f * o);
-  return !(qmin > tau + 1e-5f * S + 1e-3f);
+  const float S = r.A * mx * mx + r.C * my * my + 2.f * fabsf(r.B) * mx * my;
+  return !(qmin > r.tau + 1e-5f * S + 1e-3f);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Shared-memory ring shared by both kernels: NSTAGE record batches, `full` barriers completed by the
-// producer lanes' cp.async arrivals, `empty` barriers by one arrival per consumer warp.  Warp NCONS (the 9th)
-// is the producer: it refills a stage as soon as every consumer warp released it.
-// Consumer warps never meet at a CTA-wide barrier inside the loop, so a sub-tile with little work does not
+// producer lanes' cp.async arrivals, `empty` barriers by one arrival per consumer warp.  The last warp of the
+// CTA is the producer: it refills a stage as soon as every consumer warp released it.
+// Consumer warps never meet at a CTA-wide barrier inside the loop, so a block with little work does not
 // wait for a crowded one batch by batch.
 // ---------------------------------------------------------------------------------------------
 struct Ring {
   float4 buf[NSTAGE][STAGE_F4];
   unsigned long long full[NSTAGE];
   unsigned long long empty[NSTAGE];
-  unsigned ndone;           // consumer warps that have no pixel left (forward early exit)
-  unsigned maxc[NCONS];
+  unsigned ndone;           // forward: consumer warps that have no live pixel left
+  int stop_at;              // forward: index of the poison batch (the producer stopped before gathering it)
+  unsigned maxc[NBLK];
 };
 
-__device__ __forceinline__ void ring_init(Ring& r) {
+__device__ __forceinline__ void ring_init(Ring& r, int consumers) {
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; s++) { mbar_init(&r.full[s], 32); mbar_init(&r.empty[s], NCONS); }
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(&r.full[s], 32); mbar_init(&r.empty[s], consumers); }
     r.ndone = 0;
+    r.stop_at = -1;
     fence_mbar_init();
   }
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward
+// forward: 8 consumer warps (one 8x4 block each) + 1 producer warp
 // ---------------------------------------------------------------------------------------------
-// HALF (experimental, GSR_HALFWARP=1; NOT yet validated on a GPU -- see DESIGN.md 7b.1): every consumer warp owns two 4x4
-// blocks instead of one 8x4 block; each half-warp walks its own survivor mask, so one loop iteration composites two
-// different Gaussians and the 16-px-wide cull removes pairs the 8x4 rectangle keeps.  Per-pixel order is unchanged.
-template <bool HALF>
-__global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
-                                                               const float4* __restrict__ splat,
-                                                               float* __restrict__ out_color,
-                                                               float* __restrict__ out_depth,
-                                                               float* __restrict__ out_median,
-                                                               float* __restrict__ out_opacity) {
+constexpr int FWD_THREADS = TILE_PIX + 32;
+
+__global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
+                                                            const float4* __restrict__ splat,
+                                                            float* __restrict__ out_color,
+                                                            float* __restrict__ out_depth,
+                                                            float* __restrict__ out_median,
+                                                            float* __restrict__ out_opacity) {
   __shared__ __align__(128) Ring ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
@@ -169,90 +178,74 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
   const int n = (int)(range.y - range.x);
   const int nb = (n + RB - 1) / RB;
   const uint32_t* ids = bin.point_list + range.x;
-  ring_init(ring);
+  ring_init(ring, NBLK);
 
-  if (warp == NCONS) {
+  if (warp == NBLK) {
     // ---------------- producer warp ----------------
     int issued = 0;
     for (int b = 0; b < nb; b++) {
       const int s = b % NSTAGE;
-      bool stop = false;
+      int stop = 0;
       if (lane == 0) {
-        if (b >= NSTAGE) {
-          const unsigned par = (unsigned)((b / NSTAGE - 1) & 1);
-          while (!mbar_try(&ring.empty[s], par)) {
-            if (*(volatile unsigned*)&ring.ndone == NCONS) { stop = true; break; }
-          }
-        }
-        if (*(volatile unsigned*)&ring.ndone == NCONS) stop = true;  // every pixel of the tile is finished
+        if (b >= NSTAGE) mbar_wait(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
+        stop = *(volatile unsigned*)&ring.ndone == NBLK;  // every pixel of the tile is finished
       }
-      if (__shfl_sync(FULL, (int)stop, 0)) break;
+      if (__shfl_sync(FULL, stop, 0)) break;
       stage_gather(ring.buf[s], splat, ids + b * RB, min(RB, n - b * RB), lane, &ring.full[s]);
       issued = b + 1;
     }
     // every copy must have landed before the CTA's shared memory is released
     for (int b = max(0, issued - NSTAGE); b < issued; b++) mbar_wait(&ring.full[b % NSTAGE], (unsigned)((b / NSTAGE) & 1));
+    if (issued < nb) {
+      // poison batch: consumers parked on the batch that will never be gathered leave through it
+      if (lane == 0) *(volatile int*)&ring.stop_at = issued;
+      __syncwarp();
+      mbar_arrive(&ring.full[issued % NSTAGE]);  // 32 plain arrivals complete the phase
+    }
     return;
   }
 
-  // ---------------- consumers: warp w owns the 8x4 sub-tile at (w&1, w>>1) ----------------
+  // ---------------- consumers: warp w owns the 8x4 block at (w&1, w>>1) ----------------
   const int sx0 = tx * TILE_X + (warp & 1) * 8, sy0 = ty * TILE_Y + (warp >> 1) * 4;
-  const int px = HALF ? sx0 + 4 * (lane >> 4) + (lane & 3) : sx0 + (lane & 7);
-  const int py = HALF ? sy0 + ((lane >> 2) & 3) : sy0 + (lane >> 3);
+  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
   const float rx0 = (float)sx0, ry0 = (float)sy0;
-  const float rx1 = (float)min(sx0 + (HALF ? 3 : 7), W - 1), ry1 = (float)min(sy0 + 3, H - 1);
-  const float rbx0 = (float)(sx0 + 4), rbx1 = (float)min(sx0 + 7, W - 1);  // HALF: the right-hand 4x4 block
+  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
 
-  bool done = !inside;
-  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+  // A finished pixel (T would drop below 1e-4, forward.cu:357-362, or outside the image) is marked by the SIGN of T:
+  // T * (1 - alpha) stays negative, so it keeps failing the same test and never blends again.
+  float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
   float med_d = 15.0f, med_w = 0.f, med_id = 0.f;  // forward.cu:310-312
   unsigned last_contributor = 0;
-  bool warp_done = __all_sync(FULL, done);
+  bool warp_done = __all_sync(FULL, T < 0.f);
   if (warp_done && lane == 0) atomicAdd(&ring.ndone, 1u);
 
   for (int b = 0; b < nb; b++) {
     const int s = b % NSTAGE;
-    const unsigned par = (unsigned)((b / NSTAGE) & 1);
+    mbar_wait(&ring.full[s], (unsigned)((b / NSTAGE) & 1));
     if (warp_done) {
-      // nothing left for this warp: keep releasing stages until the whole tile is finished
-      bool stop = false;
-      while (!mbar_try(&ring.full[s], par)) {
-        if (*(volatile unsigned*)&ring.ndone == NCONS) { stop = true; break; }
-      }
-      if (stop || *(volatile unsigned*)&ring.ndone == NCONS) break;
+      // nothing left for this warp: keep releasing stages until the producer stops
+      if (*(volatile int*)&ring.stop_at == b) break;
       if (lane == 0) mbar_arrive(&ring.empty[s]);
       continue;
     }
-    mbar_wait(&ring.full[s], par);
     const int cnt = min(RB, n - b * RB);
     const float4* sb = ring.buf[s];
     for (int base = 0; base < cnt; base += 32) {
       const int j = base + lane;
       bool keep = false;
-      if (j < cnt) keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
-      unsigned mask = __ballot_sync(FULL, keep);
-      unsigned maskB = 0;
-      if constexpr (HALF) {
-        bool keepB = false;
-        if (j < cnt && rbx0 <= rbx1) keepB = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rbx0, ry0, rbx1, ry1);
-        maskB = __ballot_sync(FULL, keepB);
+      if (j < cnt) {
+        const float4 c0 = sb[j * SPLAT_F4], c1 = sb[j * SPLAT_F4 + 1];
+        keep = may_touch(cull_prep(c0, c1, sb[j * SPLAT_F4 + 2].w), rx0, ry0, rx1, ry1);
       }
-      while (HALF ? (mask | maskB) : mask) {
-        int jj;
-        if constexpr (HALF) {
-          const unsigned mine = (lane & 16) ? maskB : mask;  // each half-warp pops its own next survivor
-          jj = base + __ffs(mine) - 1;
-          mask &= mask - 1;
-          maskB &= maskB - 1;
-          if (mine == 0 || done) continue;
-        } else {
-          jj = base + __ffs(mask) - 1;
-          mask &= mask - 1;
-          if (done) continue;
-        }
-        const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
+      unsigned mask = __ballot_sync(FULL, keep);
+      const unsigned pos0 = (unsigned)(b * RB + base + 1);
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float4* rec = sb + (base + bit) * SPLAT_F4;
+        const float4 q0 = rec[0], q1 = rec[1];
         // forward.cu:343-356 with the contraction of the reference SASS
         const float dx = q0.x - pxf, dy = q0.y - pyf;
         const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
@@ -263,8 +256,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
         const float alpha = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
         if (alpha < 1.0f / 255.0f) continue;
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-        if (test_T < 0.0001f) { done = true; continue; }
-        const float4 q2 = sb[jj * SPLAT_F4 + 2];
+        if (test_T < 0.0001f) { T = -fabsf(T); continue; }
+        const float4 q2 = rec[2];
         C0 = __fmaf_rn(T, __fmul_rn(alpha, q1.w), C0);
         C1 = __fmaf_rn(T, __fmul_rn(alpha, q2.x), C1);
         C2 = __fmaf_rn(T, __fmul_rn(alpha, q2.y), C2);
@@ -275,21 +268,22 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
           med_id = (float)__float_as_int(q2.z);
         }
         T = test_T;
-        last_contributor = (unsigned)(b * RB + jj + 1);
+        last_contributor = pos0 + (unsigned)bit;
       }
-      warp_done = __all_sync(FULL, done);
+      warp_done = __all_sync(FULL, T < 0.f);
       if (warp_done) break;
     }
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(&ring.empty[s]);
       if (warp_done) atomicAdd(&ring.ndone, 1u);
+      mbar_arrive(&ring.empty[s]);
     }
   }
 
   if (inside) {
     const size_t pid = (size_t)py * W + px, HW = (size_t)W * H;
-    im.final_T[pid] = T;
+    const float Tf = fabsf(T);
+    im.final_T[pid] = Tf;
     im.n_contrib[pid] = last_contributor;
     out_color[pid] = C0;  // no background blend (forward.cu:389-390)
     out_color[HW + pid] = C1;
@@ -298,7 +292,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
     out_median[pid] = med_d;
     out_median[HW + pid] = med_w;
     out_median[2 * HW + pid] = med_id;
-    out_opacity[pid] = 1 - T;
+    out_opacity[pid] = 1 - Tf;
   }
   // largest n_contrib of the tile bounds the backward traversal
   const unsigned wmax = __reduce_max_sync(FULL, last_contributor);
@@ -307,24 +301,28 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_fwd(int W, int H, int
   if (tid == 0) {
     unsigned m = 0;
 #pragma unroll
-    for (int w = 0; w < NCONS; w++) m = max(m, ring.maxc[w]);
+    for (int w = 0; w < NBLK; w++) m = max(m, ring.maxc[w]);
     im.tile_maxc[tile] = m;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward
+// backward: 8 / NSUB consumer warps, each owning NSUB 8x4 blocks (lane = one pixel in every block), + producer
 // ---------------------------------------------------------------------------------------------
-template <bool HALF>
-__global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int gx, const float* __restrict__ bg,
-                                                               ImageView im, BinView bin,
-                                                               const float4* __restrict__ splat,
-                                                               float* __restrict__ grad,
-                                                               const float* __restrict__ dL_dpix,
-                                                               const float* __restrict__ dL_ddepthpix,
-                                                               const float* __restrict__ dL_dmedpix,
-                                                               const float* __restrict__ dL_dopacpix,
-                                                               const float ddelx_dx, const float ddely_dy) {
+// block s of warp w sits at (kx, ky) in units of (8, 4) pixels; regions are as square as possible:
+//   NSUB 1: 8x4    NSUB 2: 8x8    NSUB 4: 16x8    NSUB 8: the whole 16x16 tile
+template <int NSUB> __device__ __forceinline__ int blk_kx(int w, int s) { return NSUB <= 2 ? (w & 1) : (s & 1); }
+template <int NSUB> __device__ __forceinline__ int blk_ky(int w, int s) {
+  return NSUB == 1 ? (w >> 1) : NSUB == 2 ? (w >> 1) * 2 + s : NSUB == 4 ? w * 2 + (s >> 1) : (s >> 1);
+}
+
+template <int NSUB, int MINB>
+__global__ void __launch_bounds__((NBLK / NSUB) * 32 + 32, MINB)
+k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, BinView bin,
+             const float4* __restrict__ splat, float* __restrict__ grad, const float* __restrict__ dL_dpix,
+             const float* __restrict__ dL_ddepthpix, const float* __restrict__ dL_dmedpix,
+             const float* __restrict__ dL_dopacpix) {
+  constexpr int NCONS = NBLK / NSUB;
   __shared__ __align__(128) Ring ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
@@ -333,7 +331,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
   if (nmax == 0) return;
   const int nb = (nmax + RB - 1) / RB;
   const uint32_t* ids = bin.point_list + range.x;
-  ring_init(ring);
+  ring_init(ring, NCONS);
 
   // batch b (counted from the back) covers list positions [lo_b, hi_b), hi_b = nmax - b*RB
   if (warp == NCONS) {
@@ -350,210 +348,184 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_bwd(int W, int H, int
     return;
   }
 
-  const int sx0 = tx * TILE_X + (warp & 1) * 8, sy0 = ty * TILE_Y + (warp >> 1) * 4;
-  const int px = HALF ? sx0 + 4 * (lane >> 4) + (lane & 3) : sx0 + (lane & 7);
-  const int py = HALF ? sy0 + ((lane >> 2) & 3) : sy0 + (lane >> 3);
-  const bool inside = px < W && py < H;
-  const float pxf = (float)px, pyf = (float)py;
-  const float rx0 = (float)sx0, ry0 = (float)sy0;
-  const float rx1 = (float)min(sx0 + (HALF ? 3 : 7), W - 1), ry1 = (float)min(sy0 + 3, H - 1);
-  const float rbx0 = (float)(sx0 + 4), rbx1 = (float)min(sx0 + 7, W - 1);  // HALF: the right-hand 4x4 block
-  const size_t pid = (size_t)py * W + px, HW = (size_t)W * H;
-
-  const float T_final = inside ? im.final_T[pid] : 0.f;
-  float T = T_final;
-  const int last_contributor = inside ? (int)im.n_contrib[pid] : 0;
-  float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f, gD = 0.f, gMed = 0.f, gO = 0.f;
-  if (inside) {
-    gp0 = dL_dpix[pid]; gp1 = dL_dpix[HW + pid]; gp2 = dL_dpix[2 * HW + pid];
-    gD = dL_ddepthpix[pid];
-    gMed = dL_dmedpix[pid];  // channel 0 of the [3,H,W] median grad only (backward.cu:482, quirk 4)
-    gO = dL_dopacpix[pid];
+  // per-pixel state of the lane's NSUB pixels
+  const size_t HW = (size_t)W * H;
+  const int lx = lane & 7, ly = lane >> 3;
+  const int bx0 = tx * TILE_X, by0 = ty * TILE_Y;
+  float T[NSUB], Q[NSUB], g0[NSUB], g1[NSUB], g2[NSUB], gD[NSUB], gO[NSUB];
+  int lastc[NSUB], maxs[NSUB];
+  int warp_max = 0;
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) {
+    const int px = bx0 + blk_kx<NSUB>(warp, s) * 8 + lx, py = by0 + blk_ky<NSUB>(warp, s) * 4 + ly;
+    const bool inside = px < W && py < H;
+    const size_t pid = (size_t)py * W + px;
+    T[s] = inside ? im.final_T[pid] : 0.f;
+    lastc[s] = inside ? (int)im.n_contrib[pid] : 0;
+    g0[s] = g1[s] = g2[s] = gD[s] = gO[s] = 0.f;
+    if (inside) {
+      g0[s] = dL_dpix[pid]; g1[s] = dL_dpix[HW + pid]; g2[s] = dL_dpix[2 * HW + pid];
+      gD[s] = dL_ddepthpix[pid];
+      gO[s] = dL_dopacpix[pid];
+    }
+    // Q = (sum of s_i w_i over the contributors behind the current one) + T_final * (bg . dL_dpix): the second
+    // term is the background contribution of backward.cu:584-587, folded into the same recurrence
+    float bg_dot = 0.f;
+    bg_dot += bg[0] * g0[s]; bg_dot += bg[1] * g1[s]; bg_dot += bg[2] * g2[s];
+    Q[s] = T[s] * bg_dot;
+    maxs[s] = (int)__reduce_max_sync(FULL, (unsigned)lastc[s]);
+    warp_max = max(warp_max, maxs[s]);
   }
-  float bg_dot = 0.f;  // backward.cu:584-586
-  bg_dot += bg[0] * gp0; bg_dot += bg[1] * gp1; bg_dot += bg[2] * gp2;
-  const float bg_term = -T_final * bg_dot;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
-  float acc_d = 0.f, last_d = 0.f, acc_o = 0.f, last_o = 0.f, last_alpha = 0.f;
-  const int warp_max = (int)__reduce_max_sync(FULL, (unsigned)last_contributor);
-  // HALF: traversal bounds of the two 4x4 blocks (a block whose pixels all stopped early skips the tail entries)
-  const int maxA = HALF ? (int)__reduce_max_sync(FULL, (lane & 16) ? 0u : (unsigned)last_contributor) : 0;
-  const int maxB = HALF ? (int)__reduce_max_sync(FULL, (lane & 16) ? (unsigned)last_contributor : 0u) : 0;
-  // which lane publishes which reduced component (see the butterflies below)
-  const bool pub = HALF ? (((lane & 1) == 0) || (lane & 7) == 1) : (((lane & 3) == 0) || lane == 1 || lane == 17);
-  const int slot = HALF ? (((lane & 1) == 0) ? ((lane & 8) ? 5 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0)
-                                             : ((lane & 8) ? 9 : 4))
-                        : (((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9));
+  // which lane publishes which reduced component (see the butterfly below)
+  const bool pub = ((lane & 3) == 0) || lane == 1 || lane == 17;
+  const int slot = ((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9);
 
   for (int b = 0; b < nb; b++) {
-    const int s = b % NSTAGE;
-    mbar_wait(&ring.full[s], (unsigned)((b / NSTAGE) & 1));
+    const int st = b % NSTAGE;
+    mbar_wait(&ring.full[st], (unsigned)((b / NSTAGE) & 1));
     const int hi = nmax - b * RB, lo = max(0, hi - RB), cnt = hi - lo;
-    const float4* sb = ring.buf[s];
+    const float4* sb = ring.buf[st];
     if (lo < warp_max) {
       for (int base = 0; base < cnt; base += 32) {
         const int j = cnt - 1 - (base + lane);  // lane 0 = farthest entry of this chunk
-        bool keep = false;
-        if (j >= 0 && lo + j < (HALF ? maxA : warp_max))
-          keep = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rx0, ry0, rx1, ry1);
-        unsigned mask = __ballot_sync(FULL, keep);
-        unsigned maskB = 0;
-        if constexpr (HALF) {
-          bool keepB = false;
-          if (j >= 0 && lo + j < maxB && rbx0 <= rbx1)
-            keepB = may_touch(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], rbx0, ry0, rbx1, ry1);
-          maskB = __ballot_sync(FULL, keepB);
+        unsigned m[NSUB];
+        {
+          CullRec cr;
+          cr.live = false;
+          if (j >= 0 && lo + j < warp_max) cr = cull_prep(sb[j * SPLAT_F4], sb[j * SPLAT_F4 + 1], sb[j * SPLAT_F4 + 2].w);
+#pragma unroll
+          for (int s = 0; s < NSUB; s++) {
+            const int rxi = bx0 + blk_kx<NSUB>(warp, s) * 8, ryi = by0 + blk_ky<NSUB>(warp, s) * 4;
+            bool keep = false;
+            if (cr.live && lo + j < maxs[s] && rxi < W && ryi < H)
+              keep = may_touch(cr, (float)rxi, (float)ryi, (float)min(rxi + 7, W - 1), (float)min(ryi + 3, H - 1));
+            m[s] = __ballot_sync(FULL, keep);
+          }
         }
-        while (HALF ? (mask | maskB) : mask) {
-          int jj;
-          bool has = true;
-          if constexpr (HALF) {
-            const unsigned mine = (lane & 16) ? maskB : mask;  // each half-warp pops its own next survivor
-            has = mine != 0;
-            jj = has ? cnt - 1 - (base + __ffs(mine) - 1) : 0;
-            mask &= mask - 1;
-            maskB &= maskB - 1;
-          } else {
-            jj = cnt - 1 - (base + __ffs(mask) - 1);
-            mask &= mask - 1;
-          }
-          const float4 q0 = sb[jj * SPLAT_F4], q1 = sb[jj * SPLAT_F4 + 1];
-          const float dx = q0.x - pxf, dy = q0.y - pyf;
-          const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
-          const float t2 = __fmul_rn(dx, q0.z);
-          const float t3 = __fmul_rn(__fmul_rn(dx, q0.w), dy);
-          const float power = __fmaf_rn(__fmaf_rn(dx, t2, t1), -0.5f, -t3);
-          const float G = expf(power);
-          const float alpha = fminf(0.99f, q1.y * G);
-          // backward.cu:520-537: entries at or beyond n_contrib, power > 0 and alpha < 1/255 are skipped
-          const bool valid = has && (lo + jj < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-          unsigned vb = 0;  // HALF: which half-warps have a contributing pixel
-          if constexpr (HALF) {
-            vb = __ballot_sync(FULL, valid);
-            if (!vb) continue;
-          } else {
-            if (!__any_sync(FULL, valid)) continue;
-          }
-          const float4 q2 = sb[jj * SPLAT_F4 + 2];
+        unsigned any = m[0];
+#pragma unroll
+        for (int s = 1; s < NSUB; s++) any |= m[s];
+        while (any) {
+          const int bit = __ffs(any) - 1;
+          any &= any - 1;
+          const int jj = cnt - 1 - (base + bit);
+          const int pos = lo + jj;
+          const float4* rec = sb + jj * SPLAT_F4;
+          const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+          // v0-2 colour, v3 depth, v4 opacity, v5-6 sum u dx / u dy, v7-9 sum u dx^2 / u dx dy / u dy^2
           float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
-          if (valid) {
-            float inv;  // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: one MUFU.RCP (gradient tolerance 1e-3)
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
-            const float test_T = T * inv;
-            const float w = alpha * test_T;
-            const float oma = 1.f - last_alpha;
-            float dL_dalpha;
-            const float c0 = q1.w, c1 = q2.x, c2 = q2.y, c_d = q1.z;
-            acc0 = last_alpha * lc0 + oma * acc0; lc0 = c0; dL_dalpha = (c0 - acc0) * gp0; v0 = w * gp0;
-            acc1 = last_alpha * lc1 + oma * acc1; lc1 = c1; dL_dalpha += (c1 - acc1) * gp1; v1 = w * gp1;
-            acc2 = last_alpha * lc2 + oma * acc2; lc2 = c2; dL_dalpha += (c2 - acc2) * gp2; v2 = w * gp2;
-            acc_d = last_alpha * last_d + oma * acc_d; last_d = c_d;
-            dL_dalpha += (c_d - acc_d) * gD;
-            v3 = w * gD;
-            if (test_T > 0.5f && T < 0.5f) v3 += gMed;  // backward.cu:566-569
-            acc_o = last_alpha * last_o + oma * acc_o; last_o = 1.f;
-            dL_dalpha += (1.f - acc_o) * gO;
-            v4 = w * gO;  // direct term, backward.cu:575 (quirk 5)
-            dL_dalpha *= test_T;
-            T = test_T;
-            last_alpha = alpha;
-            dL_dalpha += bg_term * inv;  // (-T_final / (1 - alpha)) * bg_dot, backward.cu:584-587
-            const float dL_dG = q1.y * dL_dalpha;
-            const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-            const float dG_ddely = -gdy * q1.x - gdx * q0.w;
-            v5 = dL_dG * dG_ddelx * ddelx_dx;
-            v6 = dL_dG * dG_ddely * ddely_dy;
-            const float h = -0.5f * dL_dG;
-            v7 = h * gdx * dx;
-            v8 = h * gdx * dy;
-            v9 = h * gdy * dy;
-            v4 += G * dL_dalpha;
+          bool contrib = false;
+#pragma unroll
+          for (int s = 0; s < NSUB; s++) {
+            if (NSUB > 1 && !((m[s] >> bit) & 1u)) continue;  // warp-uniform
+            const float dx = q0.x - (float)(bx0 + blk_kx<NSUB>(warp, s) * 8 + lx);
+            const float dy = q0.y - (float)(by0 + blk_ky<NSUB>(warp, s) * 4 + ly);
+            const float t1 = __fmul_rn(__fmul_rn(dy, q1.x), dy);
+            const float t2 = __fmul_rn(dx, q0.z);
+            const float t3 = __fmul_rn(__fmul_rn(dx, q0.w), dy);
+            const float power = __fmaf_rn(__fmaf_rn(dx, t2, t1), -0.5f, -t3);
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, q1.y * G);
+            // backward.cu:520-537: entries at or beyond n_contrib, power > 0 and alpha < 1/255 are skipped
+            const bool valid = (pos < lastc[s]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (!__any_sync(FULL, valid)) continue;
+            contrib = true;
+            if (valid) {
+              float inv;  // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: one MUFU.RCP (gradient tolerance 1e-3)
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
+              const float Tb = T[s] * inv;  // transmittance in front of this Gaussian
+              const float w = alpha * Tb;   // its blending weight
+              // s = <this Gaussian's blended channels, the pixel's incoming gradient> (colour, depth, coverage = 1);
+              // dL/dalpha = s Tb - (sum behind of s_i w_i + bg term) / (1 - alpha)   [backward.cu:544-587 regrouped:
+              // (c - accum_rec) T == c T - (sum behind of c_i w_i) / (1 - alpha)]
+              const float sj = fmaf(q1.w, g0[s], fmaf(q2.x, g1[s], fmaf(q2.y, g2[s], fmaf(q1.z, gD[s], gO[s]))));
+              const float dL_dalpha = fmaf(sj, Tb, -(Q[s] * inv));
+              Q[s] = fmaf(sj, w, Q[s]);
+              v0 = fmaf(w, g0[s], v0);
+              v1 = fmaf(w, g1[s], v1);
+              v2 = fmaf(w, g2[s], v2);
+              v3 = fmaf(w, gD[s], v3);
+              if (Tb > 0.5f && T[s] < 0.5f) {  // backward.cu:566-569: channel 0 of the median grad only (quirk 4)
+                const int px = bx0 + blk_kx<NSUB>(warp, s) * 8 + lx, py = by0 + blk_ky<NSUB>(warp, s) * 4 + ly;
+                v3 += dL_dmedpix[(size_t)py * W + px];
+              }
+              v4 = fmaf(w, gO[s], v4);          // direct term, backward.cu:575 (quirk 5)
+              v4 = fmaf(G, dL_dalpha, v4);      // through alpha = o G
+              const float u = (q1.y * dL_dalpha) * G;  // dL/dG * G
+              const float ux = u * dx, uy = u * dy;
+              v5 += ux;
+              v6 += uy;
+              v7 = fmaf(ux, dx, v7);
+              v8 = fmaf(ux, dy, v8);
+              v9 = fmaf(uy, dy, v9);
+              T[s] = Tb;
+            }
           }
-          if constexpr (HALF) {
-            // 16-lane transposed butterfly per half-warp (12 shuffles): lane bits 8/4/2 pick the component,
-            // comp = (bit8 ? 5 : 0) + (bit4 ? 2 : 0) + (bit2 ? 1 : 0) in `c`; components 4 / 9 (by bit8) in `e`
-            const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-            float a0 = h8 ? v5 : v0, a1 = h8 ? v6 : v1, a2 = h8 ? v7 : v2, a3 = h8 ? v8 : v3, a4 = h8 ? v9 : v4;
-            a0 += __shfl_xor_sync(FULL, h8 ? v0 : v5, 8);
-            a1 += __shfl_xor_sync(FULL, h8 ? v1 : v6, 8);
-            a2 += __shfl_xor_sync(FULL, h8 ? v2 : v7, 8);
-            a3 += __shfl_xor_sync(FULL, h8 ? v3 : v8, 8);
-            a4 += __shfl_xor_sync(FULL, h8 ? v4 : v9, 8);
-            float b0 = h4 ? a2 : a0, b1 = h4 ? a3 : a1;
-            b0 += __shfl_xor_sync(FULL, h4 ? a0 : a2, 4);
-            b1 += __shfl_xor_sync(FULL, h4 ? a1 : a3, 4);
-            float e = a4 + __shfl_xor_sync(FULL, a4, 4);
-            float c = h2 ? b1 : b0;
-            c += __shfl_xor_sync(FULL, h2 ? b0 : b1, 2);
-            c += __shfl_xor_sync(FULL, c, 1);
-            e += __shfl_xor_sync(FULL, e, 2);
-            e += __shfl_xor_sync(FULL, e, 1);
-            // each half-warp publishes to its own Gaussian (q2.z differs between the halves)
-            if (pub && (vb & ((lane & 16) ? 0xffff0000u : 0x0000ffffu)))
-              atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 1) == 0) ? c : e);
-          } else {
-            // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
-            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-            float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
-            a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
-            a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
-            a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
-            a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
-            float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
-            b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
-            b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
-            float c = h4 ? b1 : b0;
-            c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
-            c += __shfl_xor_sync(FULL, c, 2);
-            c += __shfl_xor_sync(FULL, c, 1);
-            // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
-            float e = h16 ? v9 : v8;
-            e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
-            e += __shfl_xor_sync(FULL, e, 8);
-            e += __shfl_xor_sync(FULL, e, 4);
-            e += __shfl_xor_sync(FULL, e, 2);
-            e += __shfl_xor_sync(FULL, e, 1);
-            // accumulator slots: 0-2 colour, 3 depth, 4 opacity, 5-6 mean2D, 7-9 conic (xx, xy, yy)
-            if (pub) atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 3) == 0) ? c : e);
-          }
+          if (!contrib) continue;
+          // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
+          a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
+          a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
+          a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
+          a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
+          float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
+          b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
+          b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
+          float c = h4 ? b1 : b0;
+          c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
+          c += __shfl_xor_sync(FULL, c, 2);
+          c += __shfl_xor_sync(FULL, c, 1);
+          // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
+          float e = h16 ? v9 : v8;
+          e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
+          e += __shfl_xor_sync(FULL, e, 8);
+          e += __shfl_xor_sync(FULL, e, 4);
+          e += __shfl_xor_sync(FULL, e, 2);
+          e += __shfl_xor_sync(FULL, e, 1);
+          if (pub) atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 3) == 0) ? c : e);
         }
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[s]);
+    if (lane == 0) mbar_arrive(&ring.empty[st]);
   }
 }
 
 }  // namespace
 
-// Experimental half-warp compositing: opt-in with GSR_HALFWARP=1, read once per process.
-static bool halfwarp_enabled() {
-  static const bool on = [] { const char* e = getenv("GSR_HALFWARP"); return e && e[0] == '1'; }();
-  return on;
-}
-
 void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, float* out_color,
                        float* out_depth, float* out_median, float* out_opacity, cudaStream_t st) {
-  if (halfwarp_enabled())
-    k_render_fwd<true><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median,
-                                                           out_opacity);
-  else
-    k_render_fwd<false><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median,
-                                                            out_opacity);
+  k_render_fwd<<<gx * gy, FWD_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median, out_opacity);
+}
+
+// Pixels per lane of the compositing backward (1, 2, 4 or 8) and the occupancy the kernel is compiled for
+// (GSR_BWD_NSUB / GSR_BWD_MINB override the defaults, read once per process).
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int bwd_nsub() { static const int v = env_int("GSR_BWD_NSUB", 2); return v; }
+static int bwd_minb() { static const int v = env_int("GSR_BWD_MINB", 0); return v; }
+
+template <int NSUB, int MINB>
+static void launch_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
+                       const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian, const float* dL_dopacity,
+                       cudaStream_t st) {
+  k_render_bwd<NSUB, MINB><<<gx * gy, (NBLK / NSUB) * 32 + 32, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix,
+                                                                       dL_ddepth, dL_dmedian, dL_dopacity);
 }
 
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
                        const float* dL_dopacity, cudaStream_t st) {
-  // d(pixel coordinate)/d(ndc): backward.cu:493-494 (double-precision product rounded to float)
-  const float ddelx_dx = (float)(0.5 * W), ddely_dy = (float)(0.5 * H);
-  if (halfwarp_enabled())
-    k_render_bwd<true><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
-                                                           dL_dmedian, dL_dopacity, ddelx_dx, ddely_dy);
-  else
-    k_render_bwd<false><<<gx * gy, RENDER_THREADS, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix, dL_ddepth,
-                                                            dL_dmedian, dL_dopacity, ddelx_dx, ddely_dy);
+#define GSR_BWD(N, M) launch_bwd<N, M>(W, H, gx, gy, bg, im, b, g, dL_dpix, dL_ddepth, dL_dmedian, dL_dopacity, st)
+  const int n = bwd_nsub(), mb = bwd_minb();
+  if (n == 1) GSR_BWD(1, 4);
+  else if (n == 4) { if (mb == 6) GSR_BWD(4, 6); else GSR_BWD(4, 5); }
+  else if (n == 8) GSR_BWD(8, 6);
+  else { if (mb == 5) GSR_BWD(2, 5); else GSR_BWD(2, 4); }
+#undef GSR_BWD
 }
 
 }  // namespace gsr
