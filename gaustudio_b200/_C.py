@@ -29,12 +29,33 @@ def set_pipelined(enabled, slack=1.25, fixed_capacity=None):
     _pipeline.pending = []
     _pipeline.ring = None   # pinned int64 ring: one slot per in-flight view (no allocation in the hot path)
     _pipeline.slot = 0
+    _pipeline.rmax = None   # fixed-capacity mode: device-side running maximum of num_rendered (int64[1])
 
 
 def _pl():
     if not hasattr(_pipeline, "enabled"):
         set_pipelined(False)
     return _pipeline
+
+
+_PL_FIELDS = ("enabled", "fixed", "slack", "hw", "pending", "ring", "slot", "rmax")
+
+
+def pipeline_state():
+    """Snapshot of this thread's forward mode (for code that switches it temporarily, e.g. CUDA-graph capture)."""
+    pl = _pl()
+    return {k: getattr(pl, k) for k in _PL_FIELDS}
+
+
+def restore_pipeline(state):
+    for k in _PL_FIELDS:
+        setattr(_pipeline, k, state[k])
+
+
+def fixed_capacity_max():
+    """Largest num_rendered any forward needed since fixed-capacity mode was switched on (one blocking read)."""
+    pl = _pl()
+    return int(pl.rmax.item()) if pl.rmax is not None else 0
 
 
 def _quantise(r, slack):
@@ -95,17 +116,16 @@ def _f32(t, device, name):
     return t.contiguous()
 
 
-class _Arena:
-    """The three resizable byte tensors of rasterize_points.cu:27-33,74-81."""
+def _arena(device):
+    """One of the three resizable byte tensors of rasterize_points.cu:27-33,74-81 -> (callback, holder).  The ABI
+    callback is a closure over a one-element list (no object <-> bound-method cycle), so the buffer is freed by
+    reference counting as soon as autograd drops it, like the reference's tensors."""
+    holder = [torch.empty(0, dtype=torch.uint8, device=device)]
 
-    def __init__(self, device):
-        self.device = device
-        self.buf = torch.empty(0, dtype=torch.uint8, device=device)
-        self.fn = _lib.ALLOC_FN(self._alloc)
-
-    def _alloc(self, _user, nbytes):
-        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self.buf.data_ptr()
+    def alloc(_user, nbytes):
+        holder[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return holder[0].data_ptr()
+    return _lib.ALLOC_FN(alloc), holder
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
@@ -139,7 +159,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     out_color = torch.empty(3, H, W, **fopt); out_depth = torch.empty(1, H, W, **fopt)
     out_median = torch.empty(3, H, W, **fopt); out_opacity = torch.empty(1, H, W, **fopt)
     radii = torch.empty(P, dtype=torch.int32, device=dev)
-    geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+    (geom_fn, geom), (bin_fn, binning), (img_fn, img) = _arena(dev), _arena(dev), _arena(dev)
 
     pl = _pl()
     cap, host = 0, None
@@ -162,17 +182,23 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 _ptr(out_median), _ptr(out_opacity), _ptr(radii), int(bool(debug)), int(cap),
                 C.c_void_p(host.data_ptr()) if host is not None else None, C.c_void_p(stream.cuda_stream))
         if _fused is None:
-            r = L.gsr_forward(geom.fn, None, binning.fn, None, img.fn, None, P, int(degree), M, _ptr(background), W, H,
+            r = L.gsr_forward(geom_fn, None, bin_fn, None, img_fn, None, P, int(degree), M, _ptr(background), W, H,
                               _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
                               float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                               _ptr(projmatrix), _ptr(campos), *tail)
         else:
-            r = L.gsr_forward_fused(geom.fn, None, binning.fn, None, img.fn, None, P, int(degree), M, _ptr(background),
+            r = L.gsr_forward_fused(geom_fn, None, bin_fn, None, img_fn, None, P, int(degree), M, _ptr(background),
                                     W, H, _ptr(means3D), _ptr(f_dc), _ptr(f_rest), _ptr(opacity), _ptr(scales),
                                     float(scale_modifier), _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix),
                                     _ptr(campos), *tail)
         if r < 0:
             raise RuntimeError("gsr_forward failed: " + _lib.last_error())
+        if pl.enabled and pl.fixed:
+            # no host bookkeeping in this mode: the largest count any view needed is tracked on the device (the
+            # opaque image buffer starts with num_rendered as a uint64) and read by `fixed_capacity_max()`
+            if pl.rmax is None or pl.rmax.device != dev:
+                pl.rmax = torch.zeros(1, dtype=torch.int64, device=dev)
+            torch.maximum(pl.rmax, img[0][:8].view(torch.int64), out=pl.rmax)
         if pl.enabled and not pl.fixed:
             if cap > 0:
                 ev = torch.cuda.Event()
@@ -180,7 +206,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 pl.pending.append((host, ev, cap, key))
             else:  # first view of this shape ran in exact mode: seed the high-water mark
                 pl.hw[key] = _quantise(r, pl.slack)
-    return int(r), out_color, out_depth, out_median, out_opacity, radii, geom.buf, binning.buf, img.buf
+    return int(r), out_color, out_depth, out_median, out_opacity, radii, geom[0], binning[0], img[0]
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,

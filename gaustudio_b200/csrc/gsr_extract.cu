@@ -201,6 +201,7 @@ namespace gsr {
 
 struct AdamTable {
   float* p[GSR_ADAM_MAX_GROUPS]; float* g[GSR_ADAM_MAX_GROUPS]; float* m[GSR_ADAM_MAX_GROUPS]; float* v[GSR_ADAM_MAX_GROUPS];
+  float* g2[GSR_ADAM_MAX_GROUPS];  // optional second gradient tensor per group (nullptr: none)
   long long n[GSR_ADAM_MAX_GROUPS];
   float step_size[GSR_ADAM_MAX_GROUPS], decay[GSR_ADAM_MAX_GROUPS];  // lr / bc1; AdamW: 1 - lr*wd, Adam: wd
   unsigned first_block[GSR_ADAM_MAX_GROUPS + 1];
@@ -225,12 +226,18 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam(const __grid_constant__ A
   while (gi + 1 < t.groups && blockIdx.x >= t.first_block[gi + 1]) gi++;
   const long long base = (long long)(blockIdx.x - t.first_block[gi]) * ADAM_PER_BLOCK;
   float* __restrict__ P = t.p[gi]; float* __restrict__ G = t.g[gi]; float* __restrict__ M = t.m[gi]; float* __restrict__ V = t.v[gi];
+  float* __restrict__ G2 = t.g2[gi];
   const long long n = t.n[gi];
   const float ss = t.step_size[gi], dc = t.decay[gi];
   const long long i = base + threadIdx.x * 4;
   if (t.vec4[gi] && i + 3 < n) {
     float4 p = *reinterpret_cast<float4*>(P + i), g = *reinterpret_cast<float4*>(G + i);
     float4 m = *reinterpret_cast<float4*>(M + i), v = *reinterpret_cast<float4*>(V + i);
+    if (G2) {
+      const float4 h = *reinterpret_cast<float4*>(G2 + i);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+      if (zero_grad) *reinterpret_cast<float4*>(G2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     adam_one(p.x, g.x, m.x, v.x, ss, dc, b1c, b2, b2c, inv_bc2s, eps, gscale, decoupled);
     adam_one(p.y, g.y, m.y, v.y, ss, dc, b1c, b2, b2c, inv_bc2s, eps, gscale, decoupled);
     adam_one(p.z, g.z, m.z, v.z, ss, dc, b1c, b2, b2c, inv_bc2s, eps, gscale, decoupled);
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam(const __grid_constant__ A
   } else {
     for (long long k = i; k < n && k < i + 4; k++) {
       float p = P[k], g = G[k], m = M[k], v = V[k];
+      if (G2) { g += G2[k]; if (zero_grad) G2[k] = 0.f; }
       adam_one(p, g, m, v, ss, dc, b1c, b2, b2c, inv_bc2s, eps, gscale, decoupled);
       P[k] = p; M[k] = m; V[k] = v;
       if (zero_grad) G[k] = 0.f;
@@ -259,8 +267,9 @@ int launch_adam(int n_groups, const gsr_adam_group* groups, double beta1, double
     t.p[k] = q.param; t.g[k] = q.grad; t.m[k] = q.exp_avg; t.v[k] = q.exp_avg_sq; t.n[k] = q.numel;
     t.step_size[k] = (float)((double)q.lr / bc1);
     t.decay[k] = decoupled ? (float)(1.0 - (double)q.lr * (double)q.weight_decay) : q.weight_decay;
+    t.g2[k] = q.grad2;
     t.vec4[k] = ((reinterpret_cast<size_t>(q.param) | reinterpret_cast<size_t>(q.grad) | reinterpret_cast<size_t>(q.exp_avg) |
-                  reinterpret_cast<size_t>(q.exp_avg_sq)) & 15) == 0;
+                  reinterpret_cast<size_t>(q.exp_avg_sq) | reinterpret_cast<size_t>(q.grad2)) & 15) == 0;
     t.first_block[k] = blocks;
     blocks += (unsigned)((q.numel + ADAM_PER_BLOCK - 1) / ADAM_PER_BLOCK);
     k++;

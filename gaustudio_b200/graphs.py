@@ -32,9 +32,17 @@ class GraphedViewStep:
     """step = GraphedViewStep(renderer, model, loss_fn, example_cameras, capacity=None, post_fn=None)
     loss = step(camera)      # gradients of the model parameters are in their (static) .grad tensors
 
+    `step.out` is the render's result dict (static tensors, refreshed by every replay).
+
+    `loss_fn=None` captures a forward-only step (rendered under no_grad; `step(camera)` returns the result dict of
+    static output tensors, `post_fn(camera, out)`'s value is in `step.extra`) -- the extraction-pass shape of cfg 5.
+
     `capacity`: binning capacity (tile instances) baked into the graph; default = 1.3 x the largest count seen on
     `example_cameras` (rendered eagerly once each).  `step.max_rendered()` returns the largest count any replay
     needed -- compare it with `step.capacity` (an overflowing view is rendered incompletely, never out of bounds).
+
+    The fixed-capacity forward mode is only active during warm-up and capture: the caller's own forward mode
+    (`_C.set_pipelined`) is restored before the constructor returns, so eager renders afterwards behave as before.
 
     Create it BEFORE running an eager backward on the same parameter tensors: autograd binds a leaf's gradient
     accumulator to the stream of its first backward, and a legacy-default-stream binding is illegal under capture
@@ -44,49 +52,60 @@ class GraphedViewStep:
         dev = device or model._xyz.device
         self.dev, self.model = dev, model
         cams = list(example_cameras)
-        if capacity is None:  # largest instance count over the example views (eager, exact mode) + 30 %
-            _C.set_pipelined(False)
-            worst = max(self._count(renderer, cam, model, dev) for cam in cams)
-            capacity = _C._quantise(worst, 1.3)
-        self.capacity = int(capacity)
-        self.cam = _StaticCamera(cams[0], dev)
-        self.rmax = torch.zeros(1, dtype=torch.int64, device=dev)
-        params = model.parameters_list()
-        _C.set_pipelined(True, fixed_capacity=self.capacity)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
+        saved = _C.pipeline_state()
+        try:
+            if capacity is None:  # largest instance count over the example views (eager, exact mode) + 30 %
+                _C.set_pipelined(False)
+                worst = max(self._count(renderer, cam, model, dev) for cam in cams)
+                capacity = _C._quantise(worst, 1.3)
+            self.capacity = int(capacity)
+            self.cam = _StaticCamera(cams[0], dev)
+            self.train = loss_fn is not None
+            params = model.parameters_list() if self.train else []
+            _C.set_pipelined(True, fixed_capacity=self.capacity)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
 
-        def body():
-            out = renderer.render(self.cam, model)
-            loss = loss_fn(out)
-            # the header of the opaque image buffer starts with num_rendered (uint64): track its maximum on device
-            img = out["render"].grad_fn.saved_tensors[-1]
-            self.rmax.copy_(torch.maximum(self.rmax, img[:8].view(torch.int64)))
-            loss.backward()
-            extra = post_fn(self.cam, out) if post_fn is not None else None
-            return loss.detach(), extra
+            def body():
+                if not self.train:
+                    with torch.no_grad():
+                        out = renderer.render(self.cam, model)
+                        extra = post_fn(self.cam, out) if post_fn is not None else None
+                    return out, extra
+                out = renderer.render(self.cam, model)
+                self.out = out  # static output tensors of the captured step (refreshed by every replay)
+                loss = loss_fn(out)
+                loss.backward()
+                extra = post_fn(self.cam, out) if post_fn is not None else None
+                return loss.detach(), extra
 
-        with torch.cuda.stream(side):
-            for _ in range(3):  # warm-up outside capture (allocator, lazy module loads)
-                for p in params:
-                    p.grad = None
-                body()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        for p in params:
-            p.grad = None
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.extra = body()
-        self.grads = [p.grad for p in params]
-        self.rmax.zero_()
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm-up outside capture (allocator, lazy module loads)
+                    for p in params:
+                        p.grad = None
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for p in params:
+                p.grad = None
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.extra = body()
+            self.grads = [p.grad for p in params]
+            self.rmax = _C._pl().rmax  # device-side running max of num_rendered, updated inside the graph
+            self.rmax.zero_()
+        finally:
+            _C.restore_pipeline(saved)
 
     @staticmethod
     def _count(renderer, cam, model, dev):
         """num_rendered of one eager (exact-mode) forward."""
         out = renderer.render(_StaticCamera(cam, dev), model)
         fn = out["render"].grad_fn
-        return int(fn.num_rendered) if fn is not None else 0
+        if fn is None:
+            raise RuntimeError("GraphedViewStep: the model's parameters must require grad to size the capacity "
+                               "(or pass capacity= explicitly)")
+        return int(fn.num_rendered)
 
     def __call__(self, camera):
         self.cam.load(camera)

@@ -41,7 +41,7 @@ def make(config):
 
 class _AdamGroup(C.Structure):  # gsr_adam_group, include/gsr.h
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
-                ("numel", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float)]
+                ("numel", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float), ("grad2", C.c_void_p)]
 
 
 MAX_GROUPS = 16
@@ -73,22 +73,28 @@ class FusedAdam:
         betas_eps = {(g["betas"], g["eps"]) for g in self.param_groups}
         if len(betas_eps) > 1:
             raise ValueError("FusedAdam: betas and eps must be the same for every group (one launch)")
+        if not any(g["params"] for g in self.param_groups):
+            raise ValueError("optimizer got an empty parameter list")  # torch.optim's message
         self.state = {}
-        self.step_count = 0
 
     def _tensors(self):
         for g in self.param_groups:
             for p in g["params"]:
                 yield g, p
 
-    def step(self, grad_scale=1.0, zero_grad=False, closure=None):
+    def step(self, grad_scale=1.0, zero_grad=False, closure=None, extra_grads=None):
         """One optimizer step over every parameter that has a gradient.  grad_scale multiplies the gradients first
-        (1/world_size after a summing all-reduce); zero_grad=True leaves the gradients zeroed by the same kernel."""
+        (1/world_size after a summing all-reduce); zero_grad=True leaves the gradients zeroed by the same kernel.
+        extra_grads: optional list (aligned with the parameters in group order, entries may be None) of second
+        gradient tensors -- e.g. the second all-reduce bucket of a data-parallel step -- added to `.grad` inside the
+        kernel.  Like torch, every parameter keeps its own step count (bias correction of a parameter that only
+        sometimes receives a gradient); parameters that share a count move in one launch."""
         if closure is not None:
             raise ValueError("FusedAdam: closures are not supported")
-        rows, keep = [], []
+        by_step, keep = {}, []
         dev = None
-        for g, p in self._tensors():
+        extra = list(extra_grads) if extra_grads is not None else None
+        for k, (g, p) in enumerate(self._tensors()):
             if p.grad is None:
                 continue
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
@@ -96,29 +102,39 @@ class FusedAdam:
             grad = p.grad
             if not grad.is_contiguous():
                 grad = p.grad = grad.contiguous()
+            g2 = extra[k] if extra is not None and k < len(extra) else None
+            if g2 is not None and (g2.shape != p.shape or not g2.is_contiguous() or g2.dtype != torch.float32):
+                raise RuntimeError("FusedAdam: extra_grads entries must be contiguous float32 tensors shaped like their parameter")
             st = self.state.get(p)
             if st is None:
-                st = self.state[p] = {"exp_avg": torch.zeros_like(p, memory_format=torch.contiguous_format),
+                st = self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p, memory_format=torch.contiguous_format),
                                       "exp_avg_sq": torch.zeros_like(p, memory_format=torch.contiguous_format)}
+            st["step"] += 1
             dev = p.device
-            rows.append(_AdamGroup(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                                   p.numel(), float(g["lr"]), float(g["weight_decay"])))
-            keep.append(grad)
-        if not rows:
+            by_step.setdefault(st["step"], []).append(
+                _AdamGroup(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                           float(g["lr"]), float(g["weight_decay"]), g2.data_ptr() if g2 is not None else None))
+            keep.append((grad, g2))
+        if not by_step:
             return
-        self.step_count += 1
         b1, b2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
         L = _lib.lib()
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            for i in range(0, len(rows), MAX_GROUPS):
-                chunk = rows[i:i + MAX_GROUPS]
-                arr = (_AdamGroup * len(chunk))(*chunk)
-                rc = L.gsr_adam_step(len(chunk), C.cast(arr, C.c_void_p), float(b1), float(b2), float(eps), self.step_count,
-                                     int(self.decoupled), float(grad_scale), int(bool(zero_grad)), stream)
-                if rc < 0:
-                    raise RuntimeError("gsr_adam_step failed: " + _lib.last_error())
+            for step, rows in by_step.items():
+                for i in range(0, len(rows), MAX_GROUPS):
+                    chunk = rows[i:i + MAX_GROUPS]
+                    arr = (_AdamGroup * len(chunk))(*chunk)
+                    rc = L.gsr_adam_step(len(chunk), C.cast(arr, C.c_void_p), float(b1), float(b2), float(eps), int(step),
+                                         int(self.decoupled), float(grad_scale), int(bool(zero_grad)), stream)
+                    if rc < 0:
+                        raise RuntimeError("gsr_adam_step failed: " + _lib.last_error())
+
+    @property
+    def step_count(self):
+        """Largest per-parameter step count (all equal when every parameter gets a gradient every step)."""
+        return max((st["step"] for st in self.state.values()), default=0)
 
     def state_dict(self):
         """torch.optim layout: parameters are numbered in group order; state holds step / exp_avg / exp_avg_sq."""
@@ -128,12 +144,13 @@ class FusedAdam:
             d = {k: v for k, v in g.items() if k != "params"}
             d["params"] = [index[id(p)] for p in g["params"]]
             groups.append(d)
-        state = {index[id(p)]: {"step": self.step_count, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}
+        state = {index[id(p)]: {"step": st["step"], "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}
                  for p, st in self.state.items()}
         return {"state": state, "param_groups": groups, "decoupled": self.decoupled}
 
     def load_state_dict(self, sd):
-        """Resume: moments are copied onto the current parameters' devices; hyper-parameters come from the checkpoint."""
+        """Resume (also from a torch.optim.Adam/AdamW checkpoint): moments are copied onto the current parameters'
+        devices, per-parameter step counts are kept; hyper-parameters come from the checkpoint."""
         params = [p for _, p in self._tensors()]
         if [len(g["params"]) for g in sd["param_groups"]] != [len(g["params"]) for g in self.param_groups]:
             raise ValueError("FusedAdam.load_state_dict: parameter groups do not match")
@@ -141,17 +158,13 @@ class FusedAdam:
             g.update({k: v for k, v in saved.items() if k != "params"})
             g["betas"] = tuple(g["betas"])
         self.state = {}
-        steps = set()
         for i, st in sd["state"].items():
             p = params[int(i)]
             if st["exp_avg"].shape != p.shape:
                 raise ValueError("FusedAdam.load_state_dict: moment shape does not match its parameter")
-            self.state[p] = {"exp_avg": st["exp_avg"].detach().to(device=p.device, dtype=torch.float32).contiguous().clone(),
+            self.state[p] = {"step": int(st["step"]),
+                             "exp_avg": st["exp_avg"].detach().to(device=p.device, dtype=torch.float32).contiguous().clone(),
                              "exp_avg_sq": st["exp_avg_sq"].detach().to(device=p.device, dtype=torch.float32).contiguous().clone()}
-            steps.add(int(st["step"]))
-        if len(steps) > 1:
-            raise ValueError("FusedAdam.load_state_dict: one step count for all parameters (they move in one launch)")
-        self.step_count = steps.pop() if steps else 0
         self.decoupled = bool(sd.get("decoupled", self.decoupled))
 
     def zero_grad(self, set_to_none=False):

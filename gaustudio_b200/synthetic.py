@@ -36,14 +36,24 @@ class GaussianPointCloud(torch.nn.Module):
         n = len(self._f_dc)
         return torch.cat((self._f_dc.reshape(n, -1, 3), self._f_rest.reshape(n, -1, 3)), dim=1)
 
+    _ATTRS = ("_xyz", "_scale", "_rot", "_opacity", "_f_dc", "_f_rest")
+
     def to(self, device):
-        for k in ("_xyz", "_scale", "_rot", "_opacity", "_f_dc", "_f_rest"):
-            setattr(self, k, getattr(self, k).to(device))
+        for k in self._ATTRS:
+            v = getattr(self, k)
+            if isinstance(v, torch.nn.Parameter):  # registered by an optimizer plugin: move in place, stay a leaf
+                v.data = v.data.to(device)
+            else:
+                setattr(self, k, v.to(device))
         return self
 
     def requires_grad_(self, flag=True):
-        for k in ("_xyz", "_scale", "_rot", "_opacity", "_f_dc", "_f_rest"):
-            setattr(self, k, getattr(self, k).detach().requires_grad_(flag))
+        for k in self._ATTRS:
+            v = getattr(self, k)
+            if isinstance(v, torch.nn.Parameter):
+                v.requires_grad_(flag)
+            else:
+                setattr(self, k, v.detach().requires_grad_(flag))
         return self
 
     def parameters_list(self):

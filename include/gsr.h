@@ -179,6 +179,8 @@ typedef struct gsr_adam_group {
   int64_t numel;
   float lr;
   float weight_decay;
+  float* grad2; /* optional second gradient tensor (NULL: none): the step uses grad + grad2 -- two all-reduce buckets of
+                   one data-parallel step -- and zero_grad clears both */
 } gsr_adam_group;
 int gsr_adam_step(int n_groups, const gsr_adam_group* groups, double beta1, double beta2, double eps, int64_t step,
                   int decoupled, float grad_scale, int zero_grad, void* stream);

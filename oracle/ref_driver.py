@@ -7,6 +7,7 @@ Python package is not copied.  Needs a GPU to run.
 """
 import importlib.util
 import os
+from typing import NamedTuple
 
 import torch
 
@@ -28,6 +29,23 @@ def module():
         _mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(_mod)
     return _mod
+
+
+class RefSettings(NamedTuple):
+    """Field-for-field the reference's GaussianRasterizationSettings ($RAST/.../__init__.py:160-172), so the reference
+    arm of bench.py needs nothing from gaustudio_b200's rasterizer module."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
 
 
 class RefRasterize(torch.autograd.Function):

@@ -30,3 +30,11 @@ def depth2normal(depth, K, d_min=1e-3, d_max=100000.0, rot=None):
         n = (n.permute(0, 2, 3, 1) @ rot.to(n.device)).permute(0, 3, 1, 2)
     n[~vm.repeat(1, 3, 1, 1)] = -1
     return n.squeeze(0).permute(1, 2, 0)
+
+
+def gaussian_properties(model):
+    """Per-view attribute activations of the reference's vanilla renderer
+    (gaustudio/renderers/vanilla_renderer.py:28-52 with both *_python options off): exp / sigmoid / normalize through
+    the model's `get_attribute`, SH as cat(f_dc, f_rest).  -> (xyz, shs, opacity, scales, rotations)"""
+    return (model.get_attribute("xyz"), model.get_features, model.get_attribute("opacity"),
+            model.get_attribute("scale"), model.get_attribute("rot"))

@@ -99,18 +99,52 @@ def test_fused_adam_state_dict_roundtrip():
     a = torch.nn.Parameter(torch.randn(4, 3)); b = torch.nn.Parameter(torch.randn(5))
     opt = FusedAdam([{"params": [a], "lr": 0.1}, {"params": [b], "lr": 0.2, "betas": [0.9, 0.999]}], eps=1e-15)
     assert opt.param_groups[1]["betas"] == (0.9, 0.999)
-    opt.state[a] = {"exp_avg": torch.ones(4, 3), "exp_avg_sq": torch.full((4, 3), 2.0)}
-    opt.state[b] = {"exp_avg": torch.zeros(5), "exp_avg_sq": torch.zeros(5)}
-    opt.step_count = 7
+    # per-parameter step counts, like torch (b received gradients on fewer steps than a)
+    opt.state[a] = {"step": 7, "exp_avg": torch.ones(4, 3), "exp_avg_sq": torch.full((4, 3), 2.0)}
+    opt.state[b] = {"step": 5, "exp_avg": torch.zeros(5), "exp_avg_sq": torch.zeros(5)}
     sd = opt.state_dict()
-    assert sd["param_groups"][0]["params"] == [0] and sd["param_groups"][1]["params"] == [1] and sd["state"][0]["step"] == 7
+    assert sd["param_groups"][0]["params"] == [0] and sd["param_groups"][1]["params"] == [1]
+    assert sd["state"][0]["step"] == 7 and sd["state"][1]["step"] == 5
     a2 = torch.nn.Parameter(torch.randn(4, 3)); b2 = torch.nn.Parameter(torch.randn(5))
     new = FusedAdam([{"params": [a2], "lr": 1.0}, {"params": [b2], "lr": 1.0}])
     new.load_state_dict(sd)
-    assert new.step_count == 7 and new.param_groups[0]["lr"] == 0.1 and new.param_groups[1]["lr"] == 0.2
+    assert new.step_count == 7 and new.state[b2]["step"] == 5
+    assert new.param_groups[0]["lr"] == 0.1 and new.param_groups[1]["lr"] == 0.2
     assert new.param_groups[0]["eps"] == 1e-15 and torch.equal(new.state[a2]["exp_avg_sq"], torch.full((4, 3), 2.0))
     assert new.state[a2]["exp_avg"].data_ptr() != opt.state[a]["exp_avg"].data_ptr()
     with pytest.raises(ValueError):
         FusedAdam([a2]).load_state_dict(sd)
     with pytest.raises(ValueError):
         FusedAdam([{"params": [a]}, {"params": [b], "eps": 1e-8}], eps=1e-15)  # one launch: one eps
+    with pytest.raises(ValueError, match="empty parameter list"):
+        FusedAdam([])  # torch.optim raises in the same case
+
+
+def test_torch_adam_checkpoint_with_uneven_steps_loads():
+    """A torch.optim.AdamW checkpoint whose parameters have different step counts is a valid input."""
+    from gaustudio_b200.optimizers import FusedAdam
+    a = torch.nn.Parameter(torch.randn(4, 3)); b = torch.nn.Parameter(torch.randn(5))
+    ref = torch.optim.AdamW([a, b], lr=0.1)
+    a.grad = torch.randn(4, 3); b.grad = torch.randn(5); ref.step()
+    b.grad = None; a.grad = torch.randn(4, 3); ref.step()      # only `a` moves on the second step
+    sd = ref.state_dict()
+    sd["decoupled"] = True
+    opt = FusedAdam([a, b], lr=0.1)
+    opt.load_state_dict(sd)
+    assert opt.state[a]["step"] == 2 and opt.state[b]["step"] == 1
+
+
+def test_point_cloud_container_is_parameter_aware():
+    """`GeneralOptimizer` wraps the model attributes as nn.Parameters; .to() / .requires_grad_() must keep working."""
+    from gaustudio_b200 import optimizers
+    from gaustudio_b200.synthetic import make_scene
+    m = make_scene(50, 1.0, 0.05, 0)
+    with pytest.raises(ValueError, match="empty parameter list"):
+        optimizers.make({"name": "general", "model": m, "optimizer_name": "AdamW", "args": {"lr": 1e-3}})
+    optimizers.make({"name": "general", "model": m, "optimizer_name": "SGD", "args": {"lr": 1e-3},
+                     "params": {"xyz": {"lr": 1e-4}, "opacity": {"lr": 5e-2}}})
+    assert isinstance(m._xyz, torch.nn.Parameter)
+    m.requires_grad_(False)
+    assert isinstance(m._xyz, torch.nn.Parameter) and not m._xyz.requires_grad and not m._scale.requires_grad
+    m.to("cpu").requires_grad_(True)
+    assert m._xyz.is_leaf and m._xyz.requires_grad and m._scale.is_leaf

@@ -6,7 +6,7 @@ Usage: python tools/render_ab.py [cfg3] ["1 2:4 2:5 4:5 4:6 8"]"""
 import json, os, subprocess, sys, tempfile
 
 CHILD = r'''
-import sys, ctypes, math, torch
+import sys, ctypes, json, math, torch
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from gaustudio_b200 import renderers, _lib
 from gaustudio_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
