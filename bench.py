@@ -68,13 +68,13 @@ def parse():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled around and DURING the timed region (B200_PROFILING.md recipe) through NVML:
-    one sample right before the region, one right after, and a background thread every `period` seconds in between
-    (polling `nvidia-smi -lms` from a child process stalled the CUDA launch path by several ms per step on these
-    hosts; sparse NVML calls do not)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe) through NVML: a
+    background thread every `period` seconds plus one sample when the host has enqueued the last step (the GPU is
+    still executing the region then).  NVML is opened before the region.  (Polling `nvidia-smi -lms` from a child
+    process stalled the CUDA launch path by several ms per step on these hosts; sparse NVML calls do not.)"""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
-    def __init__(self, gpu_index, period=0.25):
+    def __init__(self, gpu_index, period=0.1):
         self.idx, self.period = gpu_index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop, self._thr, self._h, self._nv = None, None, None, None
@@ -123,10 +123,14 @@ class ClockSampler:
         self._thr = threading.Thread(target=loop, daemon=True)
         self._thr.start()
 
+    def mark(self):
+        """One sample now: called right after the last step was enqueued, while the GPU still executes the region."""
+        if self._h is not None:
+            self._sample()
+
     def stop(self):
         if self._h is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self._sample()  # the GPU is still finishing the region's work when the host gets here
         self._stop.set()
         self._thr.join(timeout=2)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
@@ -314,7 +318,6 @@ def run_reference(a):
     sampler = ClockSampler(dev.index).open()
     losses = torch.zeros(K, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler._sample() if sampler._h is not None else None
     sampler.start()
     e0.record()
     t0 = time.perf_counter()
@@ -322,6 +325,7 @@ def run_reference(a):
         losses[i] = step(hcams[Wn + i])
     host_enqueue_ms = (time.perf_counter() - t0) * 1e3 / K
     e1.record()
+    sampler.mark()
     torch.cuda.synchronize(dev)
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop()
@@ -469,8 +473,6 @@ def run_new(a):
     losses = torch.zeros(K, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    if sampler._h is not None:
-        sampler._sample()
     sampler.start()
     e0.record()
     t_host0 = time.perf_counter()
@@ -486,6 +488,7 @@ def run_new(a):
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K  # host time to enqueue a step (no sync inside)
     all_losses = parallel.gather_view_losses(losses, K * world, rank, world)  # the one collective
     e1.record()
+    sampler.mark()
     sync_all()
     ms_dev = parallel.barrier_max_ms(e0.elapsed_time(e1), dev)
     clocks = sampler.stop()
