@@ -85,10 +85,11 @@ def check_pipeline(wait=False):
 
 
 def _ptr(t):
-    """Device pointer of a contiguous float32/int32/uint8 tensor; None for an empty (absent) tensor."""
+    """Device address of a contiguous tensor as a plain int (ctypes converts it for a c_void_p parameter without an
+    intermediate object); None (NULL) for an absent / empty tensor."""
     if t is None or t.numel() == 0:
         return None
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()
 
 
 _bg_cache = {}
@@ -109,6 +110,8 @@ def _bg_on(t, device):
 def _f32(t, device, name):
     if t is None or t.numel() == 0:
         return t
+    if t.dtype is torch.float32 and t.device == device and t.is_contiguous():
+        return t  # the common case: nothing to do
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name} must be float32")
     if t.device != device:
@@ -116,16 +119,35 @@ def _f32(t, device, name):
     return t.contiguous()
 
 
-def _arena(device):
-    """One of the three resizable byte tensors of rasterize_points.cu:27-33,74-81 -> (callback, holder).  The ABI
-    callback is a closure over a one-element list (no object <-> bound-method cycle), so the buffer is freed by
-    reference counting as soon as autograd drops it, like the reference's tensors."""
-    holder = [torch.empty(0, dtype=torch.uint8, device=device)]
+class _on_device:
+    """`with torch.cuda.device(dev)` only when `dev` is not already current (the context manager costs ~10 us)."""
 
-    def alloc(_user, nbytes):
-        holder[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        return holder[0].data_ptr()
-    return _lib.ALLOC_FN(alloc), holder
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+# The three resizable byte tensors of rasterize_points.cu:27-33,74-81.  ONE persistent ABI callback serves every
+# call: `user` (1, 2, 3 = geometry, binning, image) selects the slot of the forward in flight on this thread, so no
+# ctypes thunk is created per view, and the buffers are plain list entries (freed by reference counting as soon as
+# autograd drops them, like the reference's tensors; no object <-> callback cycle).
+_scratch = threading.local()
+
+
+def _alloc(user, nbytes):
+    t = torch.empty(int(nbytes), dtype=torch.uint8, device=_scratch.device)
+    _scratch.slots[user] = t
+    return t.data_ptr()
+
+
+_ALLOC = _lib.ALLOC_FN(_alloc)
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
@@ -156,10 +178,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         f_dc, f_rest = (_f32(t, dev, "f_dc/f_rest") for t in _fused)
         M = 1 + (f_rest.numel() // (3 * P) if f_rest.numel() else 0)
 
-    out_color = torch.empty(3, H, W, **fopt); out_depth = torch.empty(1, H, W, **fopt)
-    out_median = torch.empty(3, H, W, **fopt); out_opacity = torch.empty(1, H, W, **fopt)
+    planes = torch.empty(8, H, W, **fopt)  # one allocation, four contiguous views
+    out_color, out_depth, out_median, out_opacity = planes[0:3], planes[3:4], planes[4:7], planes[7:8]
     radii = torch.empty(P, dtype=torch.int32, device=dev)
-    (geom_fn, geom), (bin_fn, binning), (img_fn, img) = _arena(dev), _arena(dev), _arena(dev)
+    _scratch.device, _scratch.slots = dev, {}
 
     pl = _pl()
     cap, host = 0, None
@@ -176,18 +198,18 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 check_pipeline(wait=True)
             host = pl.ring[pl.slot:pl.slot + 1]
             pl.slot = (pl.slot + 1) % 256
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = torch.cuda.current_stream(dev)
         tail = (float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), _ptr(out_color), _ptr(out_depth),
                 _ptr(out_median), _ptr(out_opacity), _ptr(radii), int(bool(debug)), int(cap),
-                C.c_void_p(host.data_ptr()) if host is not None else None, C.c_void_p(stream.cuda_stream))
+                host.data_ptr() if host is not None else None, stream.cuda_stream)
         if _fused is None:
-            r = L.gsr_forward(geom_fn, None, bin_fn, None, img_fn, None, P, int(degree), M, _ptr(background), W, H,
+            r = L.gsr_forward(_ALLOC, 1, _ALLOC, 2, _ALLOC, 3, P, int(degree), M, _ptr(background), W, H,
                               _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
                               float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                               _ptr(projmatrix), _ptr(campos), *tail)
         else:
-            r = L.gsr_forward_fused(geom_fn, None, bin_fn, None, img_fn, None, P, int(degree), M, _ptr(background),
+            r = L.gsr_forward_fused(_ALLOC, 1, _ALLOC, 2, _ALLOC, 3, P, int(degree), M, _ptr(background),
                                     W, H, _ptr(means3D), _ptr(f_dc), _ptr(f_rest), _ptr(opacity), _ptr(scales),
                                     float(scale_modifier), _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix),
                                     _ptr(campos), *tail)
@@ -198,7 +220,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             # opaque image buffer starts with num_rendered as a uint64) and read by `fixed_capacity_max()`
             if pl.rmax is None or pl.rmax.device != dev:
                 pl.rmax = torch.zeros(1, dtype=torch.int64, device=dev)
-            torch.maximum(pl.rmax, img[0][:8].view(torch.int64), out=pl.rmax)
+            torch.maximum(pl.rmax, _scratch.slots[3][:8].view(torch.int64), out=pl.rmax)
         if pl.enabled and not pl.fixed:
             if cap > 0:
                 ev = torch.cuda.Event()
@@ -206,7 +228,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 pl.pending.append((host, ev, cap, key))
             else:  # first view of this shape ran in exact mode: seed the high-water mark
                 pl.hw[key] = _quantise(r, pl.slack)
-    return int(r), out_color, out_depth, out_median, out_opacity, radii, geom[0], binning[0], img[0]
+    slots, _scratch.slots = _scratch.slots, None
+    empty = torch.empty(0, dtype=torch.uint8, device=dev)
+    return (int(r), out_color, out_depth, out_median, out_opacity, radii, slots.get(1, empty), slots.get(2, empty),
+            slots.get(3, empty))
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
@@ -233,7 +258,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         gm = _f32(dL_dout_median_depth, dev, "dL_dout_median_depth")
         go = _f32(dL_dout_final_opacity, dev, "dL_dout_final_opacity")
         radii = radii.contiguous()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             stream = torch.cuda.current_stream(dev)
             rc = L.gsr_backward(P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh),
                                 _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations),
@@ -242,7 +267,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                 _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(gm), _ptr(go), _ptr(dL_dmeans2D), None,
                                 _ptr(dL_dopacity), _ptr(dL_dcolors), None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
                                 _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), int(bool(debug)),
-                                C.c_void_p(stream.cuda_stream))
+                                stream.cuda_stream)
         if rc < 0:
             raise RuntimeError("gsr_backward failed: " + _lib.last_error())
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
@@ -270,7 +295,7 @@ def rasterize_gaussians_fused_backward(background, means3D, radii, f_dc, f_rest,
     campos = _f32(campos, dev, "campos"); background = _f32(_bg_on(background, dev), dev, "bg")
     gc = _f32(dL_dout_color, dev, "dL_dout_color"); gd = _f32(dL_dout_depth, dev, "dL_dout_depth")
     gm = _f32(dL_dout_median_depth, dev, "dL_dout_median_depth"); go = _f32(dL_dout_final_opacity, dev, "dL_dout_opacity")
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = torch.cuda.current_stream(dev)
         rc = L.gsr_backward_fused(P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(f_dc),
                                   _ptr(f_rest), _ptr(opacity_logits), _ptr(log_scales), float(scale_modifier),
@@ -278,7 +303,7 @@ def rasterize_gaussians_fused_backward(background, means3D, radii, f_dc, f_rest,
                                   float(tan_fovy), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
                                   _ptr(gc), _ptr(gd), _ptr(gm), _ptr(go), _ptr(d_m2), _ptr(d_op), _ptr(d_col), _ptr(d_m3),
                                   _ptr(d_cov), _ptr(d_dc), _ptr(d_rest), _ptr(d_sc), _ptr(d_rot), int(bool(debug)),
-                                  C.c_void_p(stream.cuda_stream))
+                                  stream.cuda_stream)
     if rc < 0:
         raise RuntimeError("gsr_backward_fused failed: " + _lib.last_error())
     return d_m2, d_op, d_m3, d_dc, d_rest, d_sc, d_rot
@@ -293,8 +318,8 @@ def mark_visible(means3D, viewmatrix, projmatrix):
         means3D = _f32(means3D, dev, "means3D")
         viewmatrix = _f32(viewmatrix, dev, "viewmatrix"); projmatrix = _f32(projmatrix, dev, "projmatrix")
         with torch.cuda.device(dev):
-            rc = L.gsr_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix), C.c_void_p(present.data_ptr()),
-                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            rc = L.gsr_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix), present.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream)
         if rc < 0:
             raise RuntimeError("gsr_mark_visible failed: " + _lib.last_error())
     return present
@@ -318,7 +343,7 @@ def debug_export(P, W, H, R, geomBuffer, binningBuffer, imageBuffer):
                                 _ptr(o["point_list"]), _ptr(o["ranges"]), _ptr(o["n_contrib"]), _ptr(o["final_T"]),
                                 _ptr(o["means2D"]), _ptr(o["conic_opacity"]), _ptr(o["depths"]), _ptr(o["rgb"]),
                                 _ptr(o["cov3D"]), _ptr(o["tiles_touched"]), _ptr(o["clamped"]),
-                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                                torch.cuda.current_stream(dev).cuda_stream)
     if rc < 0:
         raise RuntimeError("gsr_debug_export failed: " + _lib.last_error())
     return o

@@ -42,7 +42,7 @@ def build_library(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-shared", "-Xlinker", "-soname=libgsr_b200.so", "-o", LIB, *objs, "-lcudart", "-ldl"])
     text = "\n".join(log)
     with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
         f.write(text)

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 namespace gsr {
 
 namespace {
@@ -41,14 +43,20 @@ struct ProfRec { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
+const char* const kStageName[GSR_NUM_STAGES] = {"gsr:preprocess_fwd", "gsr:tile_scan", "gsr:scatter", "gsr:tile_sort",
+                                                "gsr:render_fwd", "gsr:render_bwd", "gsr:preprocess_bwd",
+                                                "gsr:depth2normal"};
+// One per stage launch: an NVTX range (timeline tools) and, when gsr_profile_enable(1), a CUDA-event pair.
 struct Prof {
   int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
   Prof(int s, cudaStream_t t) : stage(s), st(t) {
+    nvtxRangePushA(kStageName[s]);
     if (!g_prof_on) return;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, st);
   }
   ~Prof() {
+    nvtxRangePop();
     if (!a) return;
     cudaEventRecord(b, st);
     std::lock_guard<std::mutex> l(g_prof_mu);
@@ -56,6 +64,22 @@ struct Prof {
   }
 };
 }  // namespace
+
+const DeviceInfo& device_info() {
+  static DeviceInfo info[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+  DeviceInfo& d = info[dev];
+  if (d.sm_count == 0) {
+    std::lock_guard<std::mutex> l(mu);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+    d.sm_count = n;
+  }
+  return d;
+}
 
 GeomView carve_geom(char* base, int P) {
   GeomView g;

@@ -310,9 +310,13 @@ void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t s
   auto small = k_tile_sort<SORT_CAP_SMALL, 0, 512>;
   auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_SMALL, 2048>;
   constexpr int smem_small = SORT_CAP_SMALL * 8, smem_big = SORT_CAP_BIG * 8;
-  cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);  // per device
+  const DeviceInfo& di = device_info();
+  if (!di.sort_attr_set) {  // once per device
+    cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
+    di.sort_attr_set = true;
+  }
   small<<<T, SORT_THREADS, smem_small, st>>>(g, im, b);
-  big<<<148, SORT_THREADS, smem_big, st>>>(g, im, b);  // one CTA per SM, loops over hdr->num_big tiles
+  big<<<di.sm_count, SORT_THREADS, smem_big, st>>>(g, im, b);  // one CTA per SM, loops over hdr->num_big tiles
 }
 
 }  // namespace gsr

@@ -60,6 +60,14 @@ struct BinView {
   uint32_t* point_list;       // [cap] Gaussian index per sorted tile instance (== BinningState::point_list)
 };
 
+// Per-device facts and one-time kernel attributes of the CURRENT device (cached; gsr_api.cu).
+struct DeviceInfo {
+  int sm_count = 0;
+  mutable bool sort_attr_set = false;
+  mutable size_t pre_fwd_smem = 48 * 1024 - 64, pre_bwd_smem = 48 * 1024 - 64;  // dynamic smem opted into so far
+};
+const DeviceInfo& device_info();
+
 size_t geom_bytes(int P);
 size_t image_bytes(int W, int H);
 size_t binning_bytes(long long R);

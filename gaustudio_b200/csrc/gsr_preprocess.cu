@@ -639,12 +639,20 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const f
 
 void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st) {
   const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : (a.sh_rows ? (size_t)PRE_THREADS * SH_ROW * 4 : 0);
-  if (smem > 48 * 1024 - 64) cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const DeviceInfo& di = device_info();
+  if (smem > di.pre_fwd_smem) {  // opt in once per device (again only if a larger staging block shows up)
+    cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    di.pre_fwd_smem = smem;
+  }
   k_preprocess_fwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g, im);
 }
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st) {
   const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : (a.sh_rows ? (size_t)PRE_THREADS * SH_ROW * 4 : 0);
-  if (smem > 48 * 1024 - 64) cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const DeviceInfo& di = device_info();
+  if (smem > di.pre_bwd_smem) {
+    cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    di.pre_bwd_smem = smem;
+  }
   k_preprocess_bwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g);
 }
 void launch_mark_visible(int P, const float* means3D, const float* view, const float*, unsigned char* present,

@@ -505,7 +505,7 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static int bwd_nsub() { static const int v = env_int("GSR_BWD_NSUB", 2); return v; }
+static int bwd_nsub() { static const int v = env_int("GSR_BWD_NSUB", 1); return v; }
 static int bwd_minb() { static const int v = env_int("GSR_BWD_MINB", 0); return v; }
 
 template <int NSUB, int MINB>
@@ -521,10 +521,10 @@ void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView 
                        const float* dL_dopacity, cudaStream_t st) {
 #define GSR_BWD(N, M) launch_bwd<N, M>(W, H, gx, gy, bg, im, b, g, dL_dpix, dL_ddepth, dL_dmedian, dL_dopacity, st)
   const int n = bwd_nsub(), mb = bwd_minb();
-  if (n == 1) GSR_BWD(1, 4);
+  if (n == 2) { if (mb == 5) GSR_BWD(2, 5); else GSR_BWD(2, 4); }
   else if (n == 4) { if (mb == 6) GSR_BWD(4, 6); else GSR_BWD(4, 5); }
   else if (n == 8) GSR_BWD(8, 6);
-  else { if (mb == 5) GSR_BWD(2, 5); else GSR_BWD(2, 4); }
+  else { if (mb == 5) GSR_BWD(1, 5); else GSR_BWD(1, 4); }
 #undef GSR_BWD
 }
 

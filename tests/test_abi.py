@@ -47,3 +47,26 @@ def test_no_oracle_import_in_product_path():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt and "gsr_oracle" not in txt, f
+
+
+def test_header_is_plain_c():
+    """include/gsr.h is a C header: it must pass a C compiler on its own."""
+    import subprocess
+    subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", os.path.join(ROOT, "include", "gsr.h")],
+                   check=True)
+
+
+def test_reference_side_binding_compiles_against_the_header():
+    """integration/rasterize_points_gsr.cpp -- what the reference's rasterize_points.cu becomes on top of the C ABI
+     -- type-checks against include/gsr.h, the torch headers and the CUDA runtime headers."""
+    import subprocess
+    import sysconfig
+    from torch.utils import cpp_extension
+    inc = [os.path.join(ROOT, "include"), sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    inc += cpp_extension.include_paths()
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    for i in inc:
+        cmd += ["-I", i]
+    cmd.append(os.path.join(ROOT, "integration", "rasterize_points_gsr.cpp"))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
