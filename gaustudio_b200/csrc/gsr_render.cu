@@ -72,7 +72,27 @@ __device__ __forceinline__ void stage_gather(float4* dst, const float4* __restri
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// RELAXED: the waiter has nothing urgent to do (a warp whose pixels are all finished only keeps releasing stages):
+// back off with nanosleep between polls so it does not take issue slots from the warps that still composite.
+template <bool RELAXED = false>
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  if (RELAXED) {
+    while (!mbar_try(bar, parity)) __nanosleep(400);
+    return;
+  }
   const unsigned b = smem_u32(bar);
   asm volatile(
       "{\n"
@@ -187,7 +207,8 @@ __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx
       const int s = b % NSTAGE;
       int stop = 0;
       if (lane == 0) {
-        if (b >= NSTAGE) mbar_wait(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
+        // the ring is NSTAGE batches deep: the refill can afford the back-off of a relaxed wait
+        if (b >= NSTAGE) mbar_wait<true>(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
         stop = *(volatile unsigned*)&ring.ndone == NBLK;  // every pixel of the tile is finished
       }
       if (__shfl_sync(FULL, stop, 0)) break;
@@ -223,13 +244,14 @@ __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx
 
   for (int b = 0; b < nb; b++) {
     const int s = b % NSTAGE;
-    mbar_wait(&ring.full[s], (unsigned)((b / NSTAGE) & 1));
     if (warp_done) {
-      // nothing left for this warp: keep releasing stages until the producer stops
+      // nothing left for this warp: keep releasing stages (without competing for issue slots) until the producer stops
+      mbar_wait<true>(&ring.full[s], (unsigned)((b / NSTAGE) & 1));
       if (*(volatile int*)&ring.stop_at == b) break;
       if (lane == 0) mbar_arrive(&ring.empty[s]);
       continue;
     }
+    mbar_wait(&ring.full[s], (unsigned)((b / NSTAGE) & 1));
     const int cnt = min(RB, n - b * RB);
     const float4* sb = ring.buf[s];
     for (int base = 0; base < cnt; base += 32) {
@@ -338,7 +360,7 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
     for (int b = 0; b < nb; b++) {
       const int s = b % NSTAGE;
       if (b >= NSTAGE) {
-        if (lane == 0) mbar_wait(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
+        if (lane == 0) mbar_wait<true>(&ring.empty[s], (unsigned)((b / NSTAGE - 1) & 1));
         __syncwarp();
       }
       const int hi = nmax - b * RB, lo = max(0, hi - RB);

@@ -14,6 +14,8 @@ cKDTree, exactly as in the reference); its weighting runs on the device.
 """
 import ctypes as C
 
+import math
+
 import numpy as np
 import torch
 
@@ -82,9 +84,25 @@ def getNerfppNorm(cameras):
     return {"translate": -centre.flatten(), "radius": float(dist.max() * 1.1), "min_radius": float(dist.min() * 1.5)}
 
 
-def extract_view(camera, render_pkg, scene_radius, d=3, sigma_color=75, sigma_space=75):
+def _intrinsics_host(camera):
+    """(fx, fy, cx, cy) as host floats without touching the device: from the camera's FoV / size / principal point
+    (the formula of Camera.intrinsics, gaustudio/datasets/__init__.py:229-237) when it has them."""
+    if all(hasattr(camera, a) for a in ("FoVx", "FoVy", "image_width", "image_height")):
+        W, H = int(camera.image_width), int(camera.image_height)
+        pp = getattr(camera, "principal_point_ndc", None)
+        px, py = (0.5, 0.5) if pp is None else (float(pp[0]), float(pp[1]))
+        return (W / (2.0 * math.tan(camera.FoVx / 2.0)), H / (2.0 * math.tan(camera.FoVy / 2.0)), W * px, H * py)
+    K = camera.intrinsics  # a device-resident K costs one synchronising read here
+    return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+
+
+def extract_view(camera, render_pkg, scene_radius, d=3, sigma_color=75, sigma_space=75, compact=True):
     """One view of the extraction loop.  Returns dict(filtered_depth, fg_mask, cam_normals [H,W,3], valid [H,W],
-    ids [n] int64, normals [n,3] (negated world normals), confidences [n])."""
+    ids [n] int64, normals [n,3] (negated world normals), confidences [n]).
+
+    compact=True gathers the valid pixels like the reference (`ids[valid]`: a boolean-mask gather, i.e. one stream
+    synchronisation per view).  compact=False is sync-free: ids / normals / confidences cover ALL H*W pixels and the
+    invalid ones carry id -1, which `normal_fusion` skips (negative ids mean "no observation" there)."""
     opacity = render_pkg["rendered_final_opacity"][0].contiguous()
     depth = render_pkg["rendered_depth"][0]
     median_depth = render_pkg["rendered_median_depth"][0].contiguous()
@@ -93,20 +111,25 @@ def extract_view(camera, render_pkg, scene_radius, d=3, sigma_color=75, sigma_sp
     dev = opacity.device
     H, W = opacity.shape
     filtered, fg = masked_bilateral_filter(depth, opacity > 0.1, d, sigma_color, sigma_space)
-    K = camera.intrinsics
+    fx, fy, cx, cy = _intrinsics_host(camera)
     rot = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(_extrinsics_host(camera)[:3, :3]).T)).to(dev)
     cam_normals = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
     neg_world = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
     valid = torch.empty(H, W, dtype=torch.bool, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.lib().gsr_extract_normals(_ptr(filtered), _ptr(fg), _ptr(opacity), _ptr(median_depth), W, H,
-                                            float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), _ptr(rot),
+                                            float(fx), float(fy), float(cx), float(cy), _ptr(rot),
                                             float(scene_radius * 0.8), 0.5, _ptr(cam_normals), _ptr(neg_world),
                                             _ptr(valid), _stream(dev))
     if rc < 0:
         raise RuntimeError("gsr_extract_normals failed: " + _lib.last_error())
-    return {"filtered_depth": filtered, "fg_mask": fg, "cam_normals": cam_normals, "valid": valid,
-            "ids": median_ids[valid].long(), "normals": neg_world[valid], "confidences": opacity[valid]}
+    res = {"filtered_depth": filtered, "fg_mask": fg, "cam_normals": cam_normals, "valid": valid}
+    if compact:
+        res.update(ids=median_ids[valid].long(), normals=neg_world[valid], confidences=opacity[valid])
+    else:
+        res.update(ids=torch.where(valid, median_ids.long(), -1).reshape(-1), normals=neg_world.reshape(-1, 3),
+                   confidences=opacity.reshape(-1))
+    return res
 
 
 def _fusion_pass(xyz, ids_list, normals_list, conf_list, cam_ts, mean, sums, weights, touched):
@@ -132,7 +155,10 @@ def _fusion_pass(xyz, ids_list, normals_list, conf_list, cam_ts, mean, sums, wei
 
 def normal_fusion(pcd, all_ids_list, all_normals_list, all_confidences_list, cameras, smooth=True):
     """Weighted, consistency-checked fusion of per-view normals into one normal per observed Gaussian.
-    Returns (unique_ids ascending, normals [n,3]) like the reference."""
+    Returns (unique_ids ascending, normals [n,3]) like the reference.
+    Ids outside [0, P) are skipped: negative ids are the "no observation" sentinel of `extract_view(compact=False)`.
+    (The reference indexes `pcd._xyz[ids]` with them: -1 wraps to the last Gaussian and ids >= P raise; its own loop
+    never produces either, extract_pcd.py:325-337.)"""
     xyz = pcd._xyz.detach().float().contiguous()
     _need_cuda(xyz, "pcd._xyz")
     dev, P = xyz.device, xyz.shape[0]
@@ -170,7 +196,7 @@ def extract_pcd(renderer, pcd, cameras, d=3, sigma_color=75, sigma_space=75, smo
     for camera in cameras:
         with torch.no_grad():
             pkg = renderer.render(camera, pcd)
-        v = extract_view(camera, pkg, scene_radius, d, sigma_color, sigma_space)
+        v = extract_view(camera, pkg, scene_radius, d, sigma_color, sigma_space, compact=False)  # no per-view sync
         ids_l.append(v["ids"]); nrm_l.append(v["normals"]); conf_l.append(v["confidences"])
         views.append(v)
     unique_ids, normals = normal_fusion(pcd, ids_l, nrm_l, conf_l, cameras, smooth=smooth)

@@ -133,4 +133,34 @@ def test_extract_pcd_end_to_end():
     assert ok.float().mean() > 0.5
     assert torch.allclose(normals[ok].norm(dim=1), torch.ones(int(ok.sum()), device=DEV), atol=1e-4)
     # per-view lists agree with the oracle's count for one view (same kernels as test_extract_view_matches_oracle)
-    assert all(v["ids"].numel() == int(v["valid"].sum()) for v in views)
+    # (the loop runs sync-free: dense per-pixel lists, -1 where the pixel is not a valid observation)
+    assert all(int((v["ids"] >= 0).sum()) == int(v["valid"].sum()) and v["ids"].numel() == v["valid"].numel() for v in views)
+
+
+def test_dense_views_fuse_like_compact_views_and_negative_ids_are_skipped():
+    """`extract_view(compact=False)` (no boolean-mask gather, no per-view synchronisation) must fuse to the same
+    result as the reference-shaped compact lists; an id of -1 anywhere is "no observation"."""
+    from gaustudio_b200 import extract
+    model, cams, r = _scene(P=20000, K=5)
+    cams = [c.to(torch.device(DEV)) for c in cams]
+    radius = extract.getNerfppNorm(cams)["radius"]
+    lists = {True: ([], [], []), False: ([], [], [])}
+    for cam in cams:
+        with torch.no_grad():
+            pkg = r.render(cam, model)
+        for compact in (True, False):
+            v = extract.extract_view(cam, pkg, radius, compact=compact)
+            for dst, k in zip(lists[compact], ("ids", "normals", "confidences")):
+                dst.append(v[k])
+    ua, na = extract.normal_fusion(model, *lists[True], cams, smooth=False)
+    ub, nb = extract.normal_fusion(model, *lists[False], cams, smooth=False)
+    assert torch.equal(ua, ub) and ua.numel() > 100
+    assert torch.equal(torch.isnan(na), torch.isnan(nb))
+    assert torch.allclose(torch.nan_to_num(na), torch.nan_to_num(nb), atol=1e-5)
+    # a stray -1 in a compact list changes nothing
+    ids0 = torch.cat([lists[True][0][0], torch.tensor([-1], device=DEV)])
+    n0 = torch.cat([lists[True][1][0], torch.ones(1, 3, device=DEV)])
+    c0 = torch.cat([lists[True][2][0], torch.ones(1, device=DEV)])
+    uc, nc = extract.normal_fusion(model, [ids0] + lists[True][0][1:], [n0] + lists[True][1][1:], [c0] + lists[True][2][1:],
+                                   cams, smooth=False)
+    assert torch.equal(ua, uc) and torch.allclose(torch.nan_to_num(na), torch.nan_to_num(nc), atol=1e-6)

@@ -89,3 +89,31 @@ def test_training_step_through_plugins():
     assert all(torch.isfinite(p).all() for p in trained)
     assert all((p.detach() - b).abs().max() > 0 for p, b in zip(trained, before)) and torch.equal(model._f_rest, rest)
     assert sum(losses[4:]) < sum(losses[:4])  # same four views again: the loss went down
+
+
+def test_second_gradient_tensor_and_per_parameter_steps():
+    """extra_grads (the second all-reduce bucket of a data-parallel step) is summed inside the kernel and cleared by
+    zero_grad; a parameter that misses a step keeps torch's per-parameter bias correction."""
+    from gaustudio_b200.optimizers import FusedAdam
+    shapes = [(1001, 3), (257,)]
+    ours = [torch.nn.Parameter(p.clone()) for p in _params(3, shapes)]
+    ref = [torch.nn.Parameter(p.clone()) for p in _params(3, shapes)]
+    fo = FusedAdam(ours, lr=1e-2, eps=1e-12)
+    to = torch.optim.AdamW(ref, lr=1e-2, eps=1e-12)
+    for step in range(5):
+        ga, gb = _params(200 + step, shapes), _params(300 + step, shapes)
+        skip_second = step in (1, 3)  # the second parameter receives no gradient on these steps
+        extra = []
+        for i, (p, q) in enumerate(zip(ours, ref)):
+            if i == 1 and skip_second:
+                p.grad = None; q.grad = None; extra.append(None)
+                continue
+            p.grad = ga[i].clone(); extra.append(gb[i].clone())
+            q.grad = (ga[i] + gb[i]) * 0.5
+        fo.step(grad_scale=0.5, zero_grad=True, extra_grads=extra)
+        to.step()
+        for p, q, e in zip(ours, ref, extra):
+            assert torch.allclose(p, q, rtol=0, atol=3e-6 * max(1.0, float(q.abs().max())))
+            if e is not None:
+                assert float(e.abs().max()) == 0 and float(p.grad.abs().max()) == 0
+    assert fo.state[ours[0]]["step"] == 5 and fo.state[ours[1]]["step"] == 3
