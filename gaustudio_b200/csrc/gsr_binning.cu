@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   unsigned depth_bits = 0;
   if (idx < P) {
-    unpack_rect(g.rect[idx], x0, y0, x1, y1);
-    if (x1 > x0) depth_bits = __float_as_uint(g.splat[(size_t)idx * SPLAT_F4 + 1].z);
+    // both loads are issued together (the depth of a culled Gaussian is read but never used)
+    const uint2 rc = g.rect[idx];
+    depth_bits = __float_as_uint(reinterpret_cast<const float*>(g.splat + (size_t)idx * SPLAT_F4 + 1)[2]);
+    unpack_rect(rc, x0, y0, x1, y1);
   }
   const int w = x1 - x0, n = w * (y1 - y0);
   const unsigned lane = threadIdx.x & 31;
@@ -94,19 +96,22 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
     if (slot < limit) b.ents[slot] = ((unsigned long long)dbits << 32) | (unsigned)gidx;
   };
   if (n > 0 && n <= kBig) {
-    // four tiles at a time: the four returning atomics are independent and overlap their L2 round trips
+    // eight tiles at a time: the returning atomics are independent and overlap their L2 round trips (a typical
+    // splat touches 4-6 tiles, so most threads need a single round)
     const unsigned long long key = ((unsigned long long)depth_bits << 32) | (unsigned)idx;
     unsigned* cur = im.tile_cursor + subbin_of(idx) * T;
-    for (int base = 0; base < n; base += 4) {
-      unsigned slot[4];
+    constexpr int kFlight = 8;
+    for (int base = 0; base < n; base += kFlight) {
+      unsigned slot[kFlight];
+      int tx = x0 + base % w, ty = y0 + base / w;  // walk the rect row-major without a division per tile
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int i = base + k;
+      for (int k = 0; k < kFlight; k++) {
         slot[k] = 0xffffffffu;
-        if (i < n) slot[k] = atomicAdd(cur + (y0 + i / w) * gx + x0 + i % w, 1u);
+        if (base + k < n) slot[k] = atomicAdd(cur + ty * gx + tx, 1u);
+        if (++tx == x1) { tx = x0; ty++; }
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < kFlight; k++)
         if (slot[k] < limit) b.ents[slot[k]] = key;
     }
   }
