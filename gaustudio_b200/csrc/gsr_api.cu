@@ -143,6 +143,8 @@ __global__ void k_init_header(ImageHeader* h, unsigned long long cap) {
   h->capacity = cap;
   h->overflow = 0;
   h->num_big = 0;
+  h->ticket[0] = 0;
+  h->ticket[1] = 0;
 }
 
 // gaustudio/datasets/__init__.py:106-112,307-380 -- same arithmetic order as the torch ops of the reference:

@@ -28,22 +28,26 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- level 1a: tile totals + exclusive scan (one CTA; T is at most a few 10^5) --------------------
-// Tiles are taken in rounds of SCAN_THREADS consecutive tiles (coalesced, 16 independent loads per thread),
-// each round is block-scanned and chained through a running carry.
+// Every thread owns SCAN_TPT CONSECUTIVE tiles (their 32-byte runs of each sub-bin row are whole sectors), sums
+// their SUBBINS counters with all loads in flight at once, and the CTA does ONE block scan per 8192 tiles (a 1080p
+// image is a single round); the write cursors are then laid out from a second, cache-resident read of the counters.
 constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_TPT = 8;
 constexpr int SORT_CAP_SMALL_ = 4096;  // == SORT_CAP_SMALL below
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T) {
   __shared__ unsigned warp_sums[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cap = im.hdr->capacity;
   unsigned long long carry = 0;
-  for (int t0 = 0; t0 < T; t0 += SCAN_THREADS) {
-    const int t = t0 + tid;
-    unsigned cnt[SUBBINS];
-    unsigned c = 0;
+  for (int t0 = 0; t0 < T; t0 += SCAN_THREADS * SCAN_TPT) {
+    const int tb = t0 + tid * SCAN_TPT;
+    unsigned local = 0;  // instances of this thread's tiles (independent loads, all in flight together)
 #pragma unroll
-    for (int s = 0; s < SUBBINS; s++) { cnt[s] = t < T ? im.tile_count[s * T + t] : 0u; c += cnt[s]; }
-    unsigned v = c;
+    for (int s = 0; s < SUBBINS; s++)
+#pragma unroll
+      for (int k = 0; k < SCAN_TPT; k++)
+        if (tb + k < T) local += im.tile_count[s * T + tb + k];
+    unsigned v = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
     if (lane == 31) warp_sums[warp] = v;
@@ -53,16 +57,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T)
     for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, wv, o); if (lane >= o) wv += u; }
     const unsigned round_total = __shfl_sync(FULL, wv, 31);
     const unsigned before_warp = __shfl_sync(FULL, wv, max(warp - 1, 0));
-    unsigned long long run = carry + (warp ? before_warp : 0u) + (v - c);
-    if (t < T) {
-      // tiles whose segment does not fit the binning capacity render nothing (pipelined-mode overflow)
-      const bool fits = run + c <= cap;
-      im.tile_range[t] = (c && fits) ? make_uint2((unsigned)run, (unsigned)(run + c)) : make_uint2(0u, 0u);
-      if (fits && c > (unsigned)SORT_CAP_SMALL_) im.big_tiles[atomicAdd(&im.hdr->num_big, 1u)] = (unsigned)t;
+    unsigned long long run = carry + (warp ? before_warp : 0u) + (v - local);
+#pragma unroll 2
+    for (int k = 0; k < SCAN_TPT; k++) {
+      const int t = tb + k;
+      if (t < T) {
+        unsigned cnt[SUBBINS], c = 0;  // second read of the counters: L1 / L2 resident
 #pragma unroll
-      for (int s = 0; s < SUBBINS; s++) {
-        im.tile_cursor[s * T + t] = fits ? (unsigned)run : 0x80000000u;  // dropped: slots fail the range test
-        run += cnt[s];
+        for (int s = 0; s < SUBBINS; s++) { cnt[s] = im.tile_count[s * T + t]; c += cnt[s]; }
+        // tiles whose segment does not fit the binning capacity render nothing (pipelined-mode overflow)
+        const bool fits = run + c <= cap;
+        im.tile_range[t] = (c && fits) ? make_uint2((unsigned)run, (unsigned)(run + c)) : make_uint2(0u, 0u);
+        if (fits && c > (unsigned)SORT_CAP_SMALL_) im.big_tiles[atomicAdd(&im.hdr->num_big, 1u)] = (unsigned)t;
+#pragma unroll
+        for (int s = 0; s < SUBBINS; s++) {
+          im.tile_cursor[s * T + t] = fits ? (unsigned)run : 0x80000000u;  // dropped: slots fail the range test
+          run += cnt[s];
+        }
       }
     }
     carry += round_total;
@@ -136,10 +147,13 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
 // (stable by depth == ties in ascending Gaussian index) with no dependence on the scatter's arrival order.
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-// Two launches cover every tile: a small-footprint kernel (4 CTAs/SM) for tiles up to SORT_CAP_SMALL entries and
-// a one-CTA-per-SM kernel with almost all of the SM's shared memory for the crowded ones; only tiles beyond
-// SORT_CAP_BIG entries fall back to sorting in global memory (L2-resident scratch).
+// Three launches cover every tile: a small-footprint kernel (one CTA per tile, 4 CTAs/SM) for tiles up to
+// SORT_CAP_SMALL entries, a two-CTAs-per-SM kernel for tiles up to SORT_CAP_MID and a one-CTA-per-SM kernel with
+// almost all of the SM's shared memory for the most crowded ones; only tiles beyond SORT_CAP_BIG entries fall back
+// to sorting in global memory (L2-resident scratch).  The two crowded tiers take their tiles from the compact list
+// the scan produced through an atomic ticket, so a CTA that drew a 25k-entry tile does not hold up a queue of others.
 constexpr int SORT_CAP_SMALL = 4096;   // 32 KB
+constexpr int SORT_CAP_MID = 12288;    // 96 KB: two CTAs per SM
 constexpr int SORT_CAP_BIG = 26624;    // 208 KB (+ 16 KB of bucket counters)
 typedef unsigned long long u64;
 
@@ -189,20 +203,28 @@ template <int NB> struct SortShared {
   unsigned dmin, dmax;
 };
 
-// CAP: entries held in shared memory; MIN_N: tiles up to MIN_N entries belong to the other launch;
-// NB: depth buckets of the MSD split (about 8 entries per bucket at CAP).
-template <int CAP, int MIN_N, int NB>
+// CAP: entries held in shared memory; this launch owns the tiles with MIN_N < n <= MAX_N entries (MAX_N = 0: no upper
+// bound; beyond CAP the tile is sorted in the global scratch); NB: depth buckets of the MSD split; TIER: ticket index.
+template <int CAP, int MIN_N, int MAX_N, int NB, int TIER>
 __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b) {
   extern __shared__ __align__(16) u64 sort_smem[];
   __shared__ SortShared<NB> sh;
+  __shared__ unsigned sh_work;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // small launch: one CTA per tile.  big launch: a few CTAs walk the compact list of crowded tiles.
+  // small launch: one CTA per tile.  crowded launches: CTAs draw tiles from the compact list of crowded tiles.
   const unsigned num_work = MIN_N == 0 ? gridDim.x : im.hdr->num_big;
-  for (unsigned work = blockIdx.x; work < num_work; work += gridDim.x) {
+  for (unsigned work = blockIdx.x;; work += gridDim.x) {
+  if (MIN_N != 0) {
+    __syncthreads();  // everybody is done with the previous tile (and with sh_work)
+    if (tid == 0) sh_work = atomicAdd(&im.hdr->ticket[TIER], 1u);
+    __syncthreads();
+    work = sh_work;
+  }
+  if (work >= num_work) break;
   const unsigned tile = MIN_N == 0 ? work : im.big_tiles[work];
   const uint2 range = im.tile_range[tile];
   const unsigned n = range.y - range.x;
-  if (n <= (unsigned)MIN_N || (MIN_N == 0 && n > (unsigned)CAP)) continue;  // the other launch owns this tile
+  if (n <= (unsigned)MIN_N || (MAX_N != 0 && n > (unsigned)MAX_N)) continue;  // another launch owns this tile
   __syncthreads();  // shared memory of the previous tile is free
   u64* seg = b.ents + range.x;
   uint32_t* out = b.point_list + range.x;
@@ -312,16 +334,19 @@ void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, c
 }
 
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
-  auto small = k_tile_sort<SORT_CAP_SMALL, 0, 512>;
-  auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_SMALL, 2048>;
-  constexpr int smem_small = SORT_CAP_SMALL * 8, smem_big = SORT_CAP_BIG * 8;
+  auto small = k_tile_sort<SORT_CAP_SMALL, 0, SORT_CAP_SMALL, 512, 0>;
+  auto mid = k_tile_sort<SORT_CAP_MID, SORT_CAP_SMALL, SORT_CAP_MID, 512, 0>;
+  auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_MID, 0, 2048, 1>;
+  constexpr int smem_small = SORT_CAP_SMALL * 8, smem_mid = SORT_CAP_MID * 8, smem_big = SORT_CAP_BIG * 8;
   const DeviceInfo& di = device_info();
   if (!di.sort_attr_set) {  // once per device
+    cudaFuncSetAttribute(mid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mid);
     cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
     di.sort_attr_set = true;
   }
   small<<<T, SORT_THREADS, smem_small, st>>>(g, im, b);
-  big<<<di.sm_count, SORT_THREADS, smem_big, st>>>(g, im, b);  // one CTA per SM, loops over hdr->num_big tiles
+  mid<<<2 * di.sm_count, SORT_THREADS, smem_mid, st>>>(g, im, b);  // two CTAs per SM draw the 4k-12k tiles
+  big<<<di.sm_count, SORT_THREADS, smem_big, st>>>(g, im, b);      // one CTA per SM draws the rest
 }
 
 }  // namespace gsr

@@ -32,7 +32,8 @@ struct ImageHeader {            // first 256 B of the image buffer
   unsigned long long capacity;      // binning capacity the scatter / sort / render kernels may use
   unsigned int overflow;            // set when num_rendered > capacity (pipelined mode)
   unsigned int num_big;             // tiles with more instances than the small sort kernel holds
-  unsigned int pad[10];
+  unsigned int ticket[2];           // work counters of the two crowded-tile sort launches (dynamic tile hand-out)
+  unsigned int pad[8];
 };
 
 struct GeomView {      // carved from the geometry buffer, all 256-B aligned

@@ -446,47 +446,61 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
     for (int k = 0; k < 6; k++) c3[k] = cov3D[k];
     Cov2D cc;
     cov2d(mean, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, c3, a.view, cc);
-    const float x_grad_mul = cc.txtz < -cc.limx || cc.txtz > cc.limx ? 0 : 1;
-    const float y_grad_mul = cc.tytz < -cc.limy || cc.tytz > cc.limy ? 0 : 1;
+    // ---- K6 (backward.cu:144-274), derived in matrix form.  Notation (ordinary row/column math):
+    //   cov2D = [[ca, cb], [cb, cd]] = A V A^T + 0.3 I,   A = J Wr (2x3),   conic = cov2D^-1,
+    //   Gc = [[dcon_x, dcon_y], [dcon_y, dcon_w]]  (the compositing backward accumulates HALF of d/dB in dcon_y,
+    //   so Gc is the symmetric gradient matrix as it stands).
+    // d(conic) = -conic d(cov) conic  =>  dL/dcov2D = -conic Gc conic = -(adj Gc adj) / det^2, with the reference's
+    // regularised 1 / (det^2 + 1e-7).
     const float ca = cc.cov.m[0][0], cb = cc.cov.m[0][1], cd = cc.cov.m[1][1];
-    const float denom = ca * cd - cb * cb;
-    float dL_da = 0, dL_db = 0, dL_dc = 0;
-    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    const Mat3& T = cc.T;
-    if (denom2inv != 0) {
-      dL_da = denom2inv * (-cd * cd * dcon_x + 2 * cb * cd * dcon_y + (denom - ca * cd) * dcon_w);
-      dL_dc = denom2inv * (-ca * ca * dcon_w + 2 * ca * cb * dcon_y + (denom - ca * cd) * dcon_x);
-      dL_db = denom2inv * 2 * (cb * cd * dcon_x - (denom + 2 * cb * cb) * dcon_y + ca * cb * dcon_w);
-      dcv[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
-      dcv[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
-      dcv[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
-      dcv[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
-      dcv[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
-      dcv[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+    const float det = ca * cd - cb * cb;
+    const float kreg = 1.0f / ((det * det) + 0.0000001f);
+    float S00 = 0.f, S01 = 0.f, S11 = 0.f;  // dL/dcov2D (symmetric; S01 is one off-diagonal entry)
+    if (kreg != 0) {
+      const float h0 = cd * dcon_x - cb * dcon_y, h1 = cd * dcon_y - cb * dcon_w;   // row 0 of adj * Gc
+      const float h2 = ca * dcon_y - cb * dcon_x, h3 = ca * dcon_w - cb * dcon_y;   // row 1 of adj * Gc (times -1 col order)
+      S00 = -kreg * (h0 * cd - h1 * cb);
+      S01 = -kreg * (h1 * ca - h0 * cb);
+      S11 = -kreg * (h3 * ca - h2 * cb);
     }
-    const Mat3& V = cc.Vrk;
-    float dT0[3], dT1[3];
+    float A2[2][3], Vs[3][3], Wr[3][3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const float r0 = T.m[0][0] * V.m[j][0] + T.m[0][1] * V.m[j][1] + T.m[0][2] * V.m[j][2];
-      const float r1 = T.m[1][0] * V.m[j][0] + T.m[1][1] * V.m[j][1] + T.m[1][2] * V.m[j][2];
-      dT0[j] = 2 * r0 * dL_da + r1 * dL_db;
-      dT1[j] = 2 * r1 * dL_dc + r0 * dL_db;
+    for (int k = 0; k < 3; k++) {
+      A2[0][k] = cc.T.m[0][k]; A2[1][k] = cc.T.m[1][k];
+#pragma unroll
+      for (int j = 0; j < 3; j++) { Vs[k][j] = cc.Vrk.m[k][j]; Wr[k][j] = a.view[4 * j + k]; }
     }
-    const Mat3& Wm = cc.Wm;
-    const float dL_dJ00 = Wm.m[0][0] * dT0[0] + Wm.m[0][1] * dT0[1] + Wm.m[0][2] * dT0[2];
-    const float dL_dJ02 = Wm.m[2][0] * dT0[0] + Wm.m[2][1] * dT0[1] + Wm.m[2][2] * dT0[2];
-    const float dL_dJ11 = Wm.m[1][0] * dT1[0] + Wm.m[1][1] * dT1[1] + Wm.m[1][2] * dT1[2];
-    const float dL_dJ12 = Wm.m[2][0] * dT1[0] + Wm.m[2][1] * dT1[1] + Wm.m[2][2] * dT1[2];
-    const float tz = 1.f / cc.t.z, tz2 = tz * tz, tz3 = tz2 * tz;
-    const float hx = a.focal_x, hy = a.focal_y;
-    const float dL_dtx = x_grad_mul * -hx * tz2 * dL_dJ02;
-    const float dL_dty = y_grad_mul * -hy * tz2 * dL_dJ12;
-    const float dL_dtz = -hx * tz2 * dL_dJ00 - hy * tz2 * dL_dJ11 + (2 * hx * cc.t.x) * tz3 * dL_dJ02 + (2 * hy * cc.t.y) * tz3 * dL_dJ12;
+    // dL/dV = A^T S A; the packed covariance stores every off-diagonal once, so those gradients count twice
+    float SA[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { SA[0][k] = S00 * A2[0][k] + S01 * A2[1][k]; SA[1][k] = S01 * A2[0][k] + S11 * A2[1][k]; }
+    if (kreg != 0) {
+      auto dV = [&](int k, int l) { return A2[0][k] * SA[0][l] + A2[1][k] * SA[1][l]; };
+      dcv[0] = dV(0, 0); dcv[3] = dV(1, 1); dcv[5] = dV(2, 2);
+      dcv[1] = 2.f * dV(0, 1); dcv[2] = 2.f * dV(0, 2); dcv[4] = 2.f * dV(1, 2);
+    }
+    // dL/dA = 2 S A V (V symmetric), dL/dJ = dL/dA Wr^T; J = [[fx/tz, 0, -fx tx/tz^2], [0, fy/tz, -fy ty/tz^2]]
+    float dJ[2][3];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      float dA[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) dA[j] = 2.f * (SA[i][0] * Vs[0][j] + SA[i][1] * Vs[1][j] + SA[i][2] * Vs[2][j]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) dJ[i][k] = dA[0] * Wr[k][0] + dA[1] * Wr[k][1] + dA[2] * Wr[k][2];
+    }
+    const float itz = 1.f / cc.t.z, itz2 = itz * itz, itz3 = itz2 * itz;
+    const float fx = a.focal_x, fy = a.focal_y;
+    // the clamp of t.x / t.z, t.y / t.z to 1.3 tan(fov) gates the lateral gradients (backward.cu:188-191, 250-252)
+    const bool clamp_x = cc.txtz < -cc.limx || cc.txtz > cc.limx, clamp_y = cc.tytz < -cc.limy || cc.tytz > cc.limy;
+    const float dtx = clamp_x ? 0.f : -fx * itz2 * dJ[0][2];
+    const float dty = clamp_y ? 0.f : -fy * itz2 * dJ[1][2];
+    const float dtz = -fx * itz2 * dJ[0][0] - fy * itz2 * dJ[1][1] + (2.f * fx * cc.t.x) * itz3 * dJ[0][2] +
+                      (2.f * fy * cc.t.y) * itz3 * dJ[1][2];
     const float* vm = a.view;
-    dmean[0] = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;  // transformVec4x3Transpose
-    dmean[1] = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
-    dmean[2] = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
+    // t = Wr p + translation  =>  dL/dp = Wr^T dL/dt   (K6 ASSIGNS the mean gradient, K7 accumulates: quirk 7)
+#pragma unroll
+    for (int j = 0; j < 3; j++) dmean[j] = Wr[0][j] * dtx + Wr[1][j] * dty + Wr[2][j] * dtz;
 
     // ---- K7 (backward.cu:346-412)
     const float* proj = a.proj;
@@ -559,35 +573,39 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_bwd(BwdArgs a, GeomV
     }
 
     if (a.scales) {
-      // cov3D backward, backward.cu:278-341 (gradient w.r.t. the un-normalised quaternion)
+      // cov3D backward (backward.cu:278-341), derived in matrix form: Sigma = N N^T with N = R diag(s), R the standard
+      // rotation matrix of the quaternion AS GIVEN (no normalisation Jacobian: quirk 2), s = scale_modifier * scale.
+      //   dL/dN = 2 dSigma N  (dSigma symmetric: the packed off-diagonal gradients are split in two halves)
+      //   dL/ds_i = sum_r dN[r][i] R[r][i]   (taken w.r.t. the modified scale, like the reference)
+      //   dL/dR[r][i] = dN[r][i] s_i, then through the nine entries of R(q).
       float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
       float as0 = a.scales[3 * idx], as1 = a.scales[3 * idx + 1], as2 = a.scales[3 * idx + 2];
       if (a.fused) { q = act_normalize(q); as0 = expf(as0); as1 = expf(as1); as2 = expf(as2); }
       const float r = q.x, x = q.y, y = q.z, z = q.w;
-      const Mat3 R = quat_mat(r, x, y, z);
-      const float sx = a.scale_modifier * as0, sy = a.scale_modifier * as1, sz = a.scale_modifier * as2;
-      const Mat3 Mm = mmul(scale_mat(sx, sy, sz), R);
-      Mat3 dSg;
-      dSg.m[0][0] = dcv[0]; dSg.m[0][1] = 0.5f * dcv[1]; dSg.m[0][2] = 0.5f * dcv[2];
-      dSg.m[1][0] = 0.5f * dcv[1]; dSg.m[1][1] = dcv[3]; dSg.m[1][2] = 0.5f * dcv[4];
-      dSg.m[2][0] = 0.5f * dcv[2]; dSg.m[2][1] = 0.5f * dcv[4]; dSg.m[2][2] = dcv[5];
-      Mat3 M2;
+      const float Rq[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                              {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                              {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+      const float sv[3] = {a.scale_modifier * as0, a.scale_modifier * as1, a.scale_modifier * as2};
+      const float dSg[3][3] = {{dcv[0], 0.5f * dcv[1], 0.5f * dcv[2]},
+                               {0.5f * dcv[1], dcv[3], 0.5f * dcv[4]},
+                               {0.5f * dcv[2], 0.5f * dcv[4], dcv[5]}};
+      float dR[3][3];
 #pragma unroll
-      for (int c = 0; c < 3; c++)
+      for (int i = 0; i < 3; i++) {
+        float acc = 0.f;
 #pragma unroll
-        for (int rr = 0; rr < 3; rr++) M2.m[c][rr] = Mm.m[c][rr] * 2.0f;
-      const Mat3 dM = mmul(M2, dSg);
-      const Mat3 Rt = mtr(R);
-      Mat3 dMt = mtr(dM);
-      dsc[0] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-      dsc[1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-      dsc[2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
-#pragma unroll
-      for (int k = 0; k < 3; k++) { dMt.m[0][k] *= sx; dMt.m[1][k] *= sy; dMt.m[2][k] *= sz; }
-      dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
-      dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
-      dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
-      dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        for (int rr = 0; rr < 3; rr++) {
+          // dN[rr][i] = 2 sum_m dSigma[rr][m] N[m][i],  N[m][i] = R[m][i] s_i
+          const float dN = 2.f * sv[i] * (dSg[rr][0] * Rq[0][i] + dSg[rr][1] * Rq[1][i] + dSg[rr][2] * Rq[2][i]);
+          acc += dN * Rq[rr][i];
+          dR[rr][i] = dN * sv[i];
+        }
+        dsc[i] = acc;
+      }
+      dq.x = 2.f * (z * (dR[1][0] - dR[0][1]) + y * (dR[0][2] - dR[2][0]) + x * (dR[2][1] - dR[1][2]));
+      dq.y = 2.f * (y * (dR[0][1] + dR[1][0]) + z * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) - 4.f * x * (dR[1][1] + dR[2][2]);
+      dq.z = 2.f * (x * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + z * (dR[1][2] + dR[2][1])) - 4.f * y * (dR[0][0] + dR[2][2]);
+      dq.w = 2.f * (r * (dR[1][0] - dR[0][1]) + x * (dR[0][2] + dR[2][0]) + y * (dR[1][2] + dR[2][1])) - 4.f * z * (dR[0][0] + dR[1][1]);
       if (a.fused) {
         // chain through exp (scale) and F.normalize (rotation): d/dq_raw = (g - qhat (qhat . g)) / |q_raw|
         dsc[0] *= as0; dsc[1] *= as1; dsc[2] *= as2;

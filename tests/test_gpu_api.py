@@ -137,10 +137,11 @@ def test_debug_mode_empty_input_and_side_stream():
     assert z.grad is not None and z.grad.shape == (0, 3)
 
 
-@pytest.mark.parametrize("P,min_n", [(9000, 4096), (40000, 26624)])
+@pytest.mark.parametrize("P,min_n", [(9000, 4096), (24000, 12288), (40000, 26624)])
 def test_large_tile_sort_paths(P, min_n):
-    """Crowded tiles: more instances than the small sort kernel holds (-> one-CTA-per-SM kernel) and more than
-    fit in shared memory at all (-> global-memory path).  Order checked against the CPU oracle's point_list."""
+    """Crowded tiles: more instances than the small sort kernel holds (-> the two-CTAs-per-SM tier), more than that
+    tier holds (-> the one-CTA-per-SM tier) and more than fit in shared memory at all (-> global-memory path).
+    Order checked against the CPU oracle's point_list."""
     from gaustudio_b200 import _C
     from oracle.oracle import Oracle
     rng = np.random.RandomState(4)
