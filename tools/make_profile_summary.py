@@ -12,11 +12,13 @@ cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_%"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_%"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_%"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_%"),
         ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu_%"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_%"),
-        ("smsp__inst_executed.sum", "warp_inst"), ("launch__registers_per_thread", "regs"), ("lts__t_sectors_op_red.sum", "l2_red_sectors"),
-        ("lts__t_sectors_op_atom.sum", "l2_atom_sectors"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts")]
+        ("smsp__inst_executed.sum", "warp_inst"), ("launch__registers_per_thread", "regs"), ("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum", "red_sectors"),
+        ("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum", "atom_sectors"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts")]
 stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")]
-lines = [f"# ncu --set full summary ({tag}) -- cfg3 view: 1M Gaussians, 1920x1080, SH deg 3, fused activations\n",
-         f"source: `{os.path.basename(rep)}` (gpurun_out/, not committed); command: `ncu --set full --clock-control none --import-source on -k regex:k_ ... python tools/profile_one.py cfg3 3`\n",
+note = sys.argv[4] if len(sys.argv) > 4 else "cfg3 view: 1M Gaussians, 1920x1080, SH deg 3, fused activations; `ncu --set full --clock-control none --import-source on -k regex:k_ ... python tools/profile_one.py cfg3 3`"
+lines = [f"# ncu --set full summary ({tag})\n",
+         f"source: `{os.path.basename(rep)}` (gpurun_out/, not committed); {note}\n",
+         "red_sectors / atom_sectors: L1->L2 write sectors of global reductions / returning atomics (the `lts__t_sectors_op_*` counters are not exposed by this ncu build)\n",
          "| kernel | " + " | ".join(c[1] for c in cols) + " | top stalls |", "|---|" + "---|" * (len(cols) + 1)]
 traffic = {}
 for r in rows[2:]:
