@@ -28,51 +28,69 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- level 1a: tile totals + exclusive scan (one CTA; T is at most a few 10^5) --------------------
-// Every thread owns SCAN_TPT CONSECUTIVE tiles (their 32-byte runs of each sub-bin row are whole sectors), sums
-// their SUBBINS counters with all loads in flight at once, and the CTA does ONE block scan per 8192 tiles (a 1080p
-// image is a single round); the write cursors are then laid out from a second, cache-resident read of the counters.
+// Rounds of SCAN_TILES tiles (a 1080p image is one round).  Every global access is coalesced over consecutive tiles:
+//   1. tile totals (SUBBINS counters each, all loads of a thread in flight together) -> shared memory;
+//   2. ONE block scan per round: a thread scans its 8 consecutive totals in shared memory, warp / block carry;
+//   3. ranges and sub-bin write cursors, from the scanned totals and a second, cache-resident read of the counters.
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_TPT = 8;
+constexpr int SCAN_TILES = SCAN_THREADS * SCAN_TPT;
 constexpr int SORT_CAP_SMALL_ = 4096;  // == SORT_CAP_SMALL below
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T) {
+  __shared__ unsigned total[SCAN_TILES];  // tile totals, then their exclusive prefix within the round
   __shared__ unsigned warp_sums[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cap = im.hdr->capacity;
   unsigned long long carry = 0;
-  for (int t0 = 0; t0 < T; t0 += SCAN_THREADS * SCAN_TPT) {
-    const int tb = t0 + tid * SCAN_TPT;
-    unsigned local = 0;  // instances of this thread's tiles (independent loads, all in flight together)
+  for (int t0 = 0; t0 < T; t0 += SCAN_TILES) {
 #pragma unroll
-    for (int s = 0; s < SUBBINS; s++)
+    for (int k = 0; k < SCAN_TPT; k++) {
+      const int t = t0 + k * SCAN_THREADS + tid;
+      unsigned c = 0;
+      if (t < T) {
 #pragma unroll
-      for (int k = 0; k < SCAN_TPT; k++)
-        if (tb + k < T) local += im.tile_count[s * T + tb + k];
-    unsigned v = local;
+        for (int s = 0; s < SUBBINS; s++) c += im.tile_count[s * T + t];
+      }
+      total[k * SCAN_THREADS + tid] = c;
+    }
+    __syncthreads();
+    // thread `tid` scans tiles [tid * SCAN_TPT, +SCAN_TPT) of the round
+    unsigned v[SCAN_TPT], local = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
-    if (lane == 31) warp_sums[warp] = v;
+    for (int k = 0; k < SCAN_TPT; k++) { v[k] = total[tid * SCAN_TPT + k]; local += v[k]; }
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     unsigned wv = warp_sums[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, wv, o); if (lane >= o) wv += u; }
     const unsigned round_total = __shfl_sync(FULL, wv, 31);
     const unsigned before_warp = __shfl_sync(FULL, wv, max(warp - 1, 0));
-    unsigned long long run = carry + (warp ? before_warp : 0u) + (v - local);
+    unsigned run = (warp ? before_warp : 0u) + (incl - local);
+#pragma unroll
+    for (int k = 0; k < SCAN_TPT; k++) {
+      total[tid * SCAN_TPT + k] = run;  // exclusive prefix inside the round (own slots only: no hazard)
+      run += v[k];
+    }
+    __syncthreads();
 #pragma unroll 2
     for (int k = 0; k < SCAN_TPT; k++) {
-      const int t = tb + k;
+      const int t = t0 + k * SCAN_THREADS + tid;
       if (t < T) {
         unsigned cnt[SUBBINS], c = 0;  // second read of the counters: L1 / L2 resident
 #pragma unroll
         for (int s = 0; s < SUBBINS; s++) { cnt[s] = im.tile_count[s * T + t]; c += cnt[s]; }
+        unsigned long long at = carry + total[k * SCAN_THREADS + tid];
         // tiles whose segment does not fit the binning capacity render nothing (pipelined-mode overflow)
-        const bool fits = run + c <= cap;
-        im.tile_range[t] = (c && fits) ? make_uint2((unsigned)run, (unsigned)(run + c)) : make_uint2(0u, 0u);
+        const bool fits = at + c <= cap;
+        im.tile_range[t] = (c && fits) ? make_uint2((unsigned)at, (unsigned)(at + c)) : make_uint2(0u, 0u);
         if (fits && c > (unsigned)SORT_CAP_SMALL_) im.big_tiles[atomicAdd(&im.hdr->num_big, 1u)] = (unsigned)t;
 #pragma unroll
         for (int s = 0; s < SUBBINS; s++) {
-          im.tile_cursor[s * T + t] = fits ? (unsigned)run : 0x80000000u;  // dropped: slots fail the range test
-          run += cnt[s];
+          im.tile_cursor[s * T + t] = fits ? (unsigned)at : 0x80000000u;  // dropped: slots fail the range test
+          at += cnt[s];
         }
       }
     }
