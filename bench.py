@@ -572,7 +572,8 @@ def run_new(a):
     R = sum(s[0] for s in stats) / len(stats)
     R_need = sum(s[1] for s in stats) / len(stats)
     P_vis = sum(s[2] for s in stats) / len(stats)
-    ab = algorithmic_bytes(P, P_vis, D, R, R_need, W, H)
+    R_binned = sum(s[3] for s in stats) / len(stats)
+    ab = algorithmic_bytes(P, P_vis, D, R_binned, R_need, W, H)  # binning bytes: the instances really moved
     grp_ms = {"preprocess_fwd": stage_ms["preprocess_fwd"],
               "binning": stage_ms["tile_scan"] + stage_ms["scatter"] + stage_ms["tile_sort"],
               "render_fwd": stage_ms["render_fwd"]}
@@ -596,7 +597,7 @@ def run_new(a):
             "peak_source": peak_src,
             "note": "FP32/SFU-bound compositing: HBM fraction is low by construction (DESIGN.md, Roofline honesty)"}
     stages_out["_kernels_ms"] = {k: round(v, 4) for k, v in stage_ms.items()}
-    stages_out["_workload"] = {"R": R, "R_need": R_need, "P_visible": P_vis,
+    stages_out["_workload"] = {"R": R, "R_binned": R_binned, "R_need": R_need, "P_visible": P_vis,
                                "depth2normal_ms": round(stage_ms["depth2normal"], 4)}
 
     per_step = KERNELS_FWD + (KERNELS_BWD if backward else 0)
@@ -642,26 +643,30 @@ def run_new(a):
 
 
 def exact_count(_C, model, hc, dev, D, H, W, e):
-    """num_rendered of one exact-mode forward through the binding (un-fused inputs)."""
-    return view_stats(_C, model, hc, dev, D, H, W, None, e)[0]
+    """Binned tile instances of one exact-mode forward through the binding (un-fused inputs): what a fixed binning
+    capacity has to cover."""
+    view_stats(_C, model, hc, dev, D, H, W, None, e)
+    return _C.last_num_binned()
 
 
 def view_stats(_C, model, hc, dev, D, H, W, P, e):
-    """(R, R_need, P_visible) of one view; R_need = sum over tiles of the largest per-pixel n_contrib (P=None: R only)."""
+    """(R, R_need, P_visible, R_binned) of one view.  R = the reference's num_rendered (tile-rect areas), R_binned = the
+    instances that survive the exact tile culling and are really scattered / sorted, R_need = sum over tiles of the
+    largest per-pixel n_contrib (list positions the compositing kernels consume).  P=None: R only."""
     R, *_o, radii, gb, bb, ib = _C.rasterize_gaussians(
         torch.zeros(3, device=dev), model.get_attribute("xyz"), e, model.get_attribute("opacity"),
         model.get_attribute("scale"), model.get_attribute("rot"), 1.0, e, hc.world_view_transform,
         hc.full_proj_transform, math.tan(hc.FoVx * 0.5), math.tan(hc.FoVy * 0.5), H, W, model.get_features.contiguous(), D,
         hc.camera_center, False, False)
     if P is None:
-        return (R, 0, 0)
+        return (R, 0, 0, 0)
     ex = _C.debug_export(P, W, H, R, gb, bb, ib)
     nc = ex["n_contrib"]
     Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
     pad = torch.zeros(Hp, Wp, dtype=nc.dtype, device=dev)
     pad[:H, :W] = nc
     r_need = int(pad.view(Hp // 16, 16, Wp // 16, 16).amax(dim=(1, 3)).sum())
-    return (R, r_need, int((radii > 0).sum()))
+    return (R, r_need, int((radii > 0).sum()), ex["num_binned"])
 
 
 def run_dropin(a, _C, model, hcams, dev, renderers, step, K, Wn):

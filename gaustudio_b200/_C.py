@@ -52,6 +52,13 @@ def restore_pipeline(state):
         setattr(_pipeline, k, state[k])
 
 
+def last_num_binned():
+    """Tile instances the most recent EXACT-mode forward on this thread actually binned.  The returned `num_rendered`
+    keeps the reference's meaning (sum of the tile-rect areas); (Gaussian, tile) pairs that cannot reach alpha >= 1/255
+    on any pixel of the tile are not binned, so this count -- the one that sizes the binning buffer -- is smaller."""
+    return int(getattr(_scratch, "last_binned", 0))
+
+
 def fixed_capacity_max():
     """Largest num_rendered any forward needed since fixed-capacity mode was switched on (one blocking read)."""
     pl = _pl()
@@ -198,6 +205,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 check_pipeline(wait=True)
             host = pl.ring[pl.slot:pl.slot + 1]
             pl.slot = (pl.slot + 1) % 256
+    exact = cap == 0
+    if exact:  # the library also hands back the binned count (what sizes the binning buffer) through r_host
+        if getattr(_scratch, "binned", None) is None:
+            _scratch.binned = torch.zeros(1, dtype=torch.int64).pin_memory()
+        host = _scratch.binned
     with _on_device(dev):
         stream = torch.cuda.current_stream(dev)
         tail = (float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), _ptr(out_color), _ptr(out_depth),
@@ -221,13 +233,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             if pl.rmax is None or pl.rmax.device != dev:
                 pl.rmax = torch.zeros(1, dtype=torch.int64, device=dev)
             torch.maximum(pl.rmax, _scratch.slots[3][:8].view(torch.int64), out=pl.rmax)
+        if exact:
+            _scratch.last_binned = int(host[0])  # written by the library before it returned (exact mode synchronises)
         if pl.enabled and not pl.fixed:
             if cap > 0:
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 pl.pending.append((host, ev, cap, key))
             else:  # first view of this shape ran in exact mode: seed the high-water mark
-                pl.hw[key] = _quantise(r, pl.slack)
+                pl.hw[key] = _quantise(_scratch.last_binned, pl.slack)
     slots, _scratch.slots = _scratch.slots, None
     empty = torch.empty(0, dtype=torch.uint8, device=dev)
     return (int(r), out_color, out_depth, out_median, out_opacity, radii, slots.get(1, empty), slots.get(2, empty),
@@ -346,4 +360,7 @@ def debug_export(P, W, H, R, geomBuffer, binningBuffer, imageBuffer):
                                 torch.cuda.current_stream(dev).cuda_stream)
     if rc < 0:
         raise RuntimeError("gsr_debug_export failed: " + _lib.last_error())
+    # `R` is the reference's num_rendered (rect areas); the sorted list holds the binned instances only
+    o["num_binned"] = int(o["ranges"][:, 1].max()) if T else 0
+    o["point_list"] = o["point_list"][:o["num_binned"]]
     return o

@@ -90,6 +90,7 @@ GeomView carve_geom(char* base, int P) {
   take(p, g.clamped, (size_t)P);
   take(p, g.radii, (size_t)P);
   take(p, g.tiles_touched, (size_t)P);
+  take(p, g.tile_mask, (size_t)P);
   take(p, g.grad, (size_t)P * GRAD_F);
   return g;
 }
@@ -125,14 +126,14 @@ BinView carve_binning(char* base, long long cap) {
   BinView b;
   char* p = base;
   cap = round_cap(cap);
+  take(p, b.point_list, (size_t)cap + 16);
   take(p, b.ents, (size_t)cap);
   take(p, b.ents2, (size_t)cap);
-  take(p, b.point_list, (size_t)cap + 16);
   return b;
 }
 size_t binning_bytes(long long R) {
   BinView b = carve_binning(nullptr, R);
-  return reinterpret_cast<size_t>(b.point_list + (size_t)round_cap(R) + 16) + 512;
+  return reinterpret_cast<size_t>(b.ents2 + (size_t)round_cap(R)) + 512;
 }
 
 namespace {
@@ -140,6 +141,7 @@ inline char* aligned_base(char* p) { return reinterpret_cast<char*>(align_up(rei
 
 __global__ void k_init_header(ImageHeader* h, unsigned long long cap) {
   h->num_rendered = 0;
+  h->num_rect = 0;
   h->capacity = cap;
   h->overflow = 0;
   h->num_big = 0;
@@ -205,9 +207,10 @@ __global__ void k_export_geom(int P, GeomView g, float* means2D, float* conic_op
   if (tiles_touched) tiles_touched[i] = g.tiles_touched[i];
   if (clamped) { const unsigned char c = vis ? g.clamped[i] : 0; clamped[3 * i] = c & 1; clamped[3 * i + 1] = (c >> 1) & 1; clamped[3 * i + 2] = (c >> 2) & 1; }
 }
-__global__ void k_export_list(long long R, BinView b, uint32_t* point_list) {
+__global__ void k_export_list(long long R, const ImageHeader* hdr, BinView b, uint32_t* point_list) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < R) point_list[i] = b.point_list[i];
+  const long long binned = (long long)min(hdr->num_rendered, hdr->capacity);
+  if (i < R) point_list[i] = i < binned ? b.point_list[i] : 0xffffffffu;  // R is the caller's array length
 }
 __global__ void k_export_image(int N, int T, ImageView im, uint32_t* ranges, uint32_t* n_contrib, float* final_T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,7 +240,7 @@ void launch_debug_export(int P, int W, int H, long long R, GeomView g, BinView b
                          float* means2D, float* conic_opacity, float* depths, float* rgb, float* cov3D,
                          uint32_t* tiles_touched, unsigned char* clamped, cudaStream_t st) {
   if (P > 0) k_export_geom<<<(P + 255) / 256, 256, 0, st>>>(P, g, means2D, conic_opacity, depths, rgb, cov3D, tiles_touched, clamped);
-  if (R > 0 && point_list) k_export_list<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, b, point_list);
+  if (R > 0 && point_list) k_export_list<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, im.hdr, b, point_list);
   const int N = W * H, T = ((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
   k_export_image<<<(max(N, T) + 255) / 256, 256, 0, st>>>(N, T, im, ranges, n_contrib, final_T);
 }
@@ -300,17 +303,20 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
   { Prof pf(1, st); launch_tile_scan(im, T, st); }
   if (!stage_ok(dbg, st, "tile_scan")) return -1;
 
-  long long cap;
+  // Two counts: `binned` = tile instances that survive the exact tile culling (sizes the binning buffer) and the
+  // reference's num_rendered = sum of the rect areas (what the API returns in exact mode).
+  long long cap, ret;
   if (r_capacity > 0) {
-    cap = r_capacity;
+    cap = ret = r_capacity;
     if (r_host && !check(cudaMemcpyAsync(r_host, &im.hdr->num_rendered, 8, cudaMemcpyDeviceToHost, st), "async R")) return -1;
   } else {
     // exact mode: the one blocking read the reference also performs (rasterizer_impl.cu:284)
-    long long R = 0;
-    if (!check(cudaMemcpyAsync(&R, &im.hdr->num_rendered, 8, cudaMemcpyDeviceToHost, st), "read R")) return -1;
+    long long counts[2] = {0, 0};  // {binned, rect-sum}: adjacent header fields
+    if (!check(cudaMemcpyAsync(counts, &im.hdr->num_rendered, 16, cudaMemcpyDeviceToHost, st), "read R")) return -1;
     if (!check(cudaStreamSynchronize(st), "read R (sync)")) return -1;
-    if (r_host) *r_host = R;
-    cap = R;
+    if (r_host) *r_host = counts[0];
+    cap = counts[0];
+    ret = counts[1];
   }
   char* bbuf = binning_alloc(binning_user, binning_bytes(cap));
   if (!bbuf) { g_err = "gsr_forward: binning allocation failed"; return -1; }
@@ -324,7 +330,7 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
   }
   { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, g, out_color, out_depth, out_median_depth, out_opacity, st); }
   if (!stage_ok(dbg, st, "render_fwd")) return -1;
-  return cap;
+  return ret;
 }
 
 static int backward_impl(int fused, const float* f_dc, const float* f_rest, const float* opacities_raw, float* dL_df_dc, float* dL_df_rest, int P, int D, int M, int64_t R, const float* background, int width, int height,

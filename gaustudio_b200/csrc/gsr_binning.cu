@@ -107,16 +107,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T)
 __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-  unsigned depth_bits = 0;
+  unsigned depth_bits = 0, mask = 0;
   if (idx < P) {
-    // both loads are issued together (the depth of a culled Gaussian is read but never used)
+    // the three loads are issued together (the depth of a culled Gaussian is read but never used)
     const uint2 rc = g.rect[idx];
+    mask = g.tile_mask[idx];
     depth_bits = __float_as_uint(reinterpret_cast<const float*>(g.splat + (size_t)idx * SPLAT_F4 + 1)[2]);
     unpack_rect(rc, x0, y0, x1, y1);
   }
   const int w = x1 - x0, n = w * (y1 - y0);
   const unsigned lane = threadIdx.x & 31;
-  constexpr int kBig = 32;
+  constexpr int kBig = 32;  // == kBigRect of the projection kernel: larger rects are binned in full
   // cursors of tiles that were dropped for capacity start at DROPPED, so their slots fail the range test
   const unsigned long long cap = im.hdr->capacity;
   const unsigned limit = cap < 0x80000000ull ? (unsigned)cap : 0x80000000u;
@@ -125,19 +126,21 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
     if (slot < limit) b.ents[slot] = ((unsigned long long)dbits << 32) | (unsigned)gidx;
   };
   if (n > 0 && n <= kBig) {
-    // eight tiles at a time: the returning atomics are independent and overlap their L2 round trips (a typical
-    // splat touches 4-6 tiles, so most threads need a single round)
+    // eight binned tiles at a time: the returning atomics are independent and overlap their L2 round trips (a typical
+    // splat keeps 2-4 of its tiles, so most threads need a single round)
     const unsigned long long key = ((unsigned long long)depth_bits << 32) | (unsigned)idx;
     unsigned* cur = im.tile_cursor + subbin_of(idx) * T;
     constexpr int kFlight = 8;
-    for (int base = 0; base < n; base += kFlight) {
+    while (mask) {
       unsigned slot[kFlight];
-      int tx = x0 + base % w, ty = y0 + base / w;  // walk the rect row-major without a division per tile
 #pragma unroll
       for (int k = 0; k < kFlight; k++) {
         slot[k] = 0xffffffffu;
-        if (base + k < n) slot[k] = atomicAdd(cur + ty * gx + tx, 1u);
-        if (++tx == x1) { tx = x0; ty++; }
+        if (mask) {
+          const int i = __ffs(mask) - 1;
+          mask &= mask - 1;
+          slot[k] = atomicAdd(cur + (y0 + i / w) * gx + x0 + i % w, 1u);
+        }
       }
 #pragma unroll
       for (int k = 0; k < kFlight; k++)

@@ -28,12 +28,13 @@ constexpr int SPLAT_BYTES = 48;
 constexpr int GRAD_F = 12;  // per-Gaussian screen-space gradient accumulator (10 used), 48 B
 
 struct ImageHeader {            // first 256 B of the image buffer
-  unsigned long long num_rendered;  // R = sum of tile counts (written by the scan kernel)
+  unsigned long long num_rendered;  // binned tile instances = sum of the tile histogram (written by the scan kernel)
+  unsigned long long num_rect;      // the reference's num_rendered: sum of the tile-rect areas (projection kernel)
   unsigned long long capacity;      // binning capacity the scatter / sort / render kernels may use
   unsigned int overflow;            // set when num_rendered > capacity (pipelined mode)
   unsigned int num_big;             // tiles with more instances than the small sort kernel holds
   unsigned int ticket[2];           // work counters of the two crowded-tile sort launches (dynamic tile hand-out)
-  unsigned int pad[8];
+  unsigned int pad[6];
 };
 
 struct GeomView {      // carved from the geometry buffer, all 256-B aligned
@@ -42,7 +43,8 @@ struct GeomView {      // carved from the geometry buffer, all 256-B aligned
   float* cov3D;        // [P][6]
   unsigned char* clamped;  // [P] bit c set <=> channel c was clamped (forward.cu:66-68)
   int* radii;          // [P] (internal copy; the caller's radii array is also written)
-  uint32_t* tiles_touched;  // [P]
+  uint32_t* tiles_touched;  // [P] area of the tile rect (the reference's tiles_touched)
+  uint32_t* tile_mask;      // [P] rects of <= 32 tiles: bit i set <=> tile i (row-major in the rect) is binned
   float* grad;         // [P][GRAD_F] backward scratch
 };
 struct ImageView {
@@ -55,10 +57,10 @@ struct ImageView {
   uint32_t* tile_maxc;    // [T] max n_contrib over the tile's pixels (bounds the backward traversal)
   uint32_t* big_tiles;    // [T] compact list of crowded tiles (hdr->num_big entries), built by the scan
 };
-struct BinView {
+struct BinView {               // point_list comes FIRST: its address does not depend on the capacity (backward, export)
+  uint32_t* point_list;       // [cap] Gaussian index per sorted tile instance (== BinningState::point_list)
   unsigned long long* ents;   // [cap] (depth bits << 32 | gaussian index), grouped by tile (level-1 output)
   unsigned long long* ents2;  // [cap] scratch of the level-2 sort for tiles that exceed shared memory
-  uint32_t* point_list;       // [cap] Gaussian index per sorted tile instance (== BinningState::point_list)
 };
 
 // Per-device facts and one-time kernel attributes of the CURRENT device (cached; gsr_api.cu).
@@ -144,6 +146,55 @@ __device__ __forceinline__ uint2 pack_rect(int xmin, int ymin, int xmax, int yma
 }
 __device__ __forceinline__ void unpack_rect(uint2 r, int& xmin, int& ymin, int& xmax, int& ymax) {
   xmin = r.x & 0xffff; xmax = r.x >> 16; ymin = r.y & 0xffff; ymax = r.y >> 16;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conservative rectangle test, shared by the binning (16x16 tiles) and the compositing kernels (8x4 blocks).
+// Returns false only if alpha = min(0.99, o*exp(power)) < 1/255 for EVERY pixel centre in [rx0,rx1]x[ry0,ry1] (the
+// reference skips such pairs, forward.cu:353-355 / backward.cu:535-537).
+// With q(d) = A dx^2 + 2B dx dy + C dy^2 = -2*power, alpha >= 1/255 needs q <= tau = 2 ln(255 o) (stored in
+// the record by the projection kernel).  q is convex (conic positive definite), so its minimum over the
+// rectangle is 0 if the centre is inside, else it lies on an edge facing the centre; each facing edge is a
+// 1-D quadratic minimised in closed form.  The edge minimiser uses an approximate reciprocal: an error in the
+// minimiser's position only enters q to second order (and not at all when it is clamped to a corner).  The
+// margin covers the rounding of the per-pixel evaluation (relative 1e-5 of the largest term magnitude + 1e-3
+// absolute); any non-finite / non-PD / extreme input keeps the pair.
+// ---------------------------------------------------------------------------------------------
+struct CullRec {
+  float gx, gy, A, B, C, tau, nBiC, nBiA;  // nBiC = -B / C, nBiA = -B / A
+  bool live, odd;                          // live: opacity can reach 1/255 at all; odd: keep unconditionally
+};
+__device__ __forceinline__ CullRec cull_prep(const float4 q0, const float4 q1, const float tau) {
+  CullRec r;
+  r.gx = q0.x; r.gy = q0.y; r.A = q0.z; r.B = q0.w; r.C = q1.x; r.tau = tau;
+  r.live = !(q1.y < 0.0039f);  // alpha <= o < 1/255 everywhere (exp(power) <= 1)
+  r.odd = !(r.A > 1e-30f && r.C > 1e-30f && r.A * r.C - r.B * r.B > 0.f && r.A < 1e30f && r.C < 1e30f);
+  float iC, iA;  // A, C in (1e-30, 1e30) whenever the values are used: plain MUFU.RCP is safe
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iC) : "f"(r.C));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(r.A));
+  r.nBiC = -r.B * iC;
+  r.nBiA = -r.B * iA;
+  return r;
+}
+__device__ __forceinline__ bool may_touch(const CullRec& r, float rx0, float ry0, float rx1, float ry1) {
+  if (!r.live) return false;
+  const float dxlo = r.gx - rx1, dxhi = r.gx - rx0, dylo = r.gy - ry1, dyhi = r.gy - ry0;
+  const bool inx = dxlo <= 0.f && dxhi >= 0.f, iny = dylo <= 0.f && dyhi >= 0.f;
+  if ((inx && iny) || r.odd) return true;
+  float qmin = 3.0e38f;
+  if (!inx) {
+    const float dxe = dxlo > 0.f ? dxlo : dxhi;
+    const float dys = fminf(fmaxf(r.nBiC * dxe, dylo), dyhi);
+    qmin = r.A * dxe * dxe + 2.f * r.B * dxe * dys + r.C * dys * dys;
+  }
+  if (!iny) {
+    const float dye = dylo > 0.f ? dylo : dyhi;
+    const float dxs = fminf(fmaxf(r.nBiA * dye, dxlo), dxhi);
+    qmin = fminf(qmin, r.A * dxs * dxs + 2.f * r.B * dxs * dye + r.C * dye * dye);
+  }
+  const float mx = fmaxf(fabsf(dxlo), fabsf(dxhi)), my = fmaxf(fabsf(dylo), fabsf(dyhi));
+  const float S = r.A * mx * mx + r.C * my * my + 2.f * fabsf(r.B) * mx * my;
+  return !(qmin > r.tau + 1e-5f * S + 1e-3f);
 }
 
 // 5-point cross normal of Camera.depth2normal (gaustudio/datasets/__init__.py:106-112,307-380, k = 3), same

@@ -169,19 +169,23 @@ __device__ __forceinline__ void cov2d(const V3& mean, float fx, float fy, float 
   o.cov.m[1][1] += 0.3f;
 }
 
-// Count / scatter helper: visits every tile of every lane's rect.  Lanes with small rects loop themselves;
-// large rects (a splat covering much of the screen) are walked by the whole warp so one thread never
-// serialises thousands of atomics (the reference's duplicateWithKeys does, rasterizer_impl.cu:98-108).
+// Count helper: visits the binned tiles of every lane's rect.  Lanes with small rects (<= 32 tiles) loop themselves over
+// the set bits of their tile mask; large rects (a splat covering much of the screen) are walked in full by the
+// whole warp so one thread never serialises thousands of atomics (the reference's duplicateWithKeys does,
+// rasterizer_impl.cu:98-108).
+constexpr int kBigRect = 32;
 template <typename F>
-__device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, int gx, F f) {
+__device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, uint32_t mask, int gx, F f) {
   const int w = x1 - x0, n = w * (y1 - y0);
   const unsigned lane = threadIdx.x & 31;
-  constexpr int kBig = 32;
-  if (n > 0 && n <= kBig) {
-    for (int y = y0; y < y1; y++)
-      for (int x = x0; x < x1; x++) f(y * gx + x, lane);
+  if (n > 0 && n <= kBigRect) {
+    while (mask) {
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      f((y0 + i / w) * gx + x0 + i % w, lane);
+    }
   }
-  unsigned big = __ballot_sync(0xffffffffu, n > kBig);
+  unsigned big = __ballot_sync(0xffffffffu, n > kBigRect);
   while (big) {
     const int src = __ffs(big) - 1;
     big &= big - 1;
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
   __shared__ __align__(8) unsigned long long sh_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  uint32_t tiles = 0, tmask = 0xffffffffu;  // rect area (the reference's tiles_touched) and which of those tiles are binned
   // whole CTA inside the array, coefficients beyond DC needed -> TMA staging
   const bool bulk = a.sh_bulk && a.D > 0 && (blockIdx.x + 1) * PRE_THREADS <= a.P;
   const int rest_row = (a.M - 1) * 3;
@@ -220,7 +225,6 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
   }
   if (idx < a.P) {
     int radius_i = 0;
-    uint32_t tiles = 0;
     const V3 p = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
     // in_frustum (auxiliary.h:139-164): only the near plane is tested
     const V3 p_view = xf4x3(p, a.view);
@@ -333,10 +337,25 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
           g.clamped[idx] = cl;
           float4* s = g.splat + (size_t)idx * SPLAT_F4;
           const float opac = a.fused ? act_sigmoid(a.opacities[idx]) : a.opacities[idx];
-          // tau = 2 ln(255 o): alpha >= 1/255 needs the conic form <= tau (block cull of the compositing kernels)
-          s[0] = make_float4(px, py, conA, conB);
-          s[1] = make_float4(conC, opac, p_view.z, rgb[0]);
-          s[2] = make_float4(rgb[1], rgb[2], __int_as_float(idx), 2.f * logf(255.f * opac));
+          // tau = 2 ln(255 o): alpha >= 1/255 needs the conic form <= tau (rectangle test of gsr_internal.cuh)
+          const float4 r0 = make_float4(px, py, conA, conB), r1 = make_float4(conC, opac, p_view.z, rgb[0]);
+          const float tau = 2.f * logf(255.f * opac);
+          s[0] = r0;
+          s[1] = r1;
+          s[2] = make_float4(rgb[1], rgb[2], __int_as_float(idx), tau);
+          // Exact tile culling: a (Gaussian, tile) pair of the reference's rect is binned only if the Gaussian can
+          // reach alpha >= 1/255 on some pixel of that tile.  For every other pair the reference `continue`s on all
+          // 256 pixels (forward.cu:353-355), so dropping it changes no output -- only the internal lists get shorter.
+          if (tiles <= (uint32_t)kBigRect) {
+            const CullRec cr = cull_prep(r0, r1, tau);
+            tmask = 0;
+            int i = 0;
+            for (int ty = y0; ty < y1; ty++)
+              for (int tx = x0; tx < x1; tx++, i++)
+                if (may_touch(cr, (float)(tx * TILE_X), (float)(ty * TILE_Y), (float)min(tx * TILE_X + TILE_X - 1, a.W - 1),
+                              (float)min(ty * TILE_Y + TILE_Y - 1, a.H - 1)))
+                  tmask |= 1u << i;
+          }
         }
       }
     }
@@ -344,12 +363,18 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
     g.radii[idx] = radius_i;
     if (a.radii_out) a.radii_out[idx] = radius_i;
     g.tiles_touched[idx] = tiles;
+    g.tile_mask[idx] = tmask;
     g.rect[idx] = pack_rect(x0, y0, x1, y1);
+  }
+  // the reference's num_rendered (sum of the rect areas, rasterizer_impl.cu:280-284): one atomic per warp
+  {
+    const unsigned wsum = __reduce_add_sync(0xffffffffu, tiles);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&im.hdr->num_rect, (unsigned long long)wsum);
   }
   // per-tile instance histogram (level 1 of the two-level binning; replaces InclusiveSum +
   // duplicateWithKeys offsets, rasterizer_impl.cu:280-300)
   const int T = a.gx * a.gy, warp_base = idx - (int)(threadIdx.x & 31);
-  for_each_tile(x0, y0, x1, y1, a.gx, [&](int tile, unsigned src) {
+  for_each_tile(x0, y0, x1, y1, tmask, a.gx, [&](int tile, unsigned src) {
     atomicAdd(&im.tile_count[subbin_of(warp_base + (int)src) * T + tile], 1u);
   });
   if ((bulk || rows) && threadIdx.x == 0) bar_wait0(&sh_bar);  // the copies must have landed before the CTA retires

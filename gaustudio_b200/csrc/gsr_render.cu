@@ -107,52 +107,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// Conservative block test.  Returns false only if alpha = min(0.99, o*exp(power)) < 1/255 for EVERY pixel
-// centre in [rx0,rx1]x[ry0,ry1] (the reference skips such pairs, forward.cu:353-355 / backward.cu:535-537).
-// With q(d) = A dx^2 + 2B dx dy + C dy^2 = -2*power, alpha >= 1/255 needs q <= tau = 2 ln(255 o) (stored in
-// the record by the projection kernel).  q is convex (conic positive definite), so its minimum over the
-// rectangle is 0 if the centre is inside, else it lies on an edge facing the centre; each facing edge is a
-// 1-D quadratic minimised in closed form.  The edge minimiser uses an approximate reciprocal: an error in the
-// minimiser's position only enters q to second order (and not at all when it is clamped to a corner).  The
-// margin covers the rounding of the per-pixel evaluation (relative 1e-5 of the largest term magnitude + 1e-3
-// absolute); any non-finite / non-PD / extreme input keeps the pair.
-struct CullRec {
-  float gx, gy, A, B, C, tau, nBiC, nBiA;  // nBiC = -B / C, nBiA = -B / A
-  bool live, odd;                          // live: opacity can reach 1/255 at all; odd: keep unconditionally
-};
-__device__ __forceinline__ CullRec cull_prep(const float4 q0, const float4 q1, const float tau) {
-  CullRec r;
-  r.gx = q0.x; r.gy = q0.y; r.A = q0.z; r.B = q0.w; r.C = q1.x; r.tau = tau;
-  r.live = !(q1.y < 0.0039f);  // alpha <= o < 1/255 everywhere (exp(power) <= 1)
-  r.odd = !(r.A > 1e-30f && r.C > 1e-30f && r.A * r.C - r.B * r.B > 0.f && r.A < 1e30f && r.C < 1e30f);
-  float iC, iA;  // A, C in (1e-30, 1e30) whenever the values are used: plain MUFU.RCP is safe
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iC) : "f"(r.C));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(r.A));
-  r.nBiC = -r.B * iC;
-  r.nBiA = -r.B * iA;
-  return r;
-}
-__device__ __forceinline__ bool may_touch(const CullRec& r, float rx0, float ry0, float rx1, float ry1) {
-  if (!r.live) return false;
-  const float dxlo = r.gx - rx1, dxhi = r.gx - rx0, dylo = r.gy - ry1, dyhi = r.gy - ry0;
-  const bool inx = dxlo <= 0.f && dxhi >= 0.f, iny = dylo <= 0.f && dyhi >= 0.f;
-  if ((inx && iny) || r.odd) return true;
-  float qmin = 3.0e38f;
-  if (!inx) {
-    const float dxe = dxlo > 0.f ? dxlo : dxhi;
-    const float dys = fminf(fmaxf(r.nBiC * dxe, dylo), dyhi);
-    qmin = r.A * dxe * dxe + 2.f * r.B * dxe * dys + r.C * dys * dys;
-  }
-  if (!iny) {
-    const float dye = dylo > 0.f ? dylo : dyhi;
-    const float dxs = fminf(fmaxf(r.nBiA * dye, dxlo), dxhi);
-    qmin = fminf(qmin, r.A * dxs * dxs + 2.f * r.B * dxs * dye + r.C * dye * dye);
-  }
-  const float mx = fmaxf(fabsf(dxlo), fabsf(dxhi)), my = fmaxf(fabsf(dylo), fabsf(dyhi));
-  const float S = r.A * mx * mx + r.C * my * my + 2.f * fabsf(r.B) * mx * my;
-  return !(qmin > r.tau + 1e-5f * S + 1e-3f);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Shared-memory ring shared by both kernels: NSTAGE record batches, `full` barriers completed by the
 // producer lanes' cp.async arrivals, `empty` barriers by one arrival per consumer warp.  The last warp of the

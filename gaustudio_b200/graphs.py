@@ -105,7 +105,7 @@ class GraphedViewStep:
         if fn is None:
             raise RuntimeError("GraphedViewStep: the model's parameters must require grad to size the capacity "
                                "(or pass capacity= explicitly)")
-        return int(fn.num_rendered)
+        return _C.last_num_binned()  # what sizes the binning buffer (fn.num_rendered keeps the reference's meaning)
 
     def __call__(self, camera):
         self.cam.load(camera)

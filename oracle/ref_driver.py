@@ -114,3 +114,19 @@ def parse_binning(binning, R):
     base = binning.data_ptr()
     start = ((base + 127) & ~127) - base
     return binning[start:start + 4 * R].view(torch.int32)
+
+
+def parse_image_ranges(img, num_pixels, num_tiles):
+    """Per-tile [start, end) of ImageState::fromChunk (rasterizer_impl.cu:173-180): accum_alpha f32[N], n_contrib
+    u32[N], ranges uint2[N] (allocated for N = W*H entries, the first `num_tiles` are used), each 128-byte aligned."""
+    base = img.data_ptr()
+    off = 0
+
+    def take(nbytes):
+        nonlocal off
+        start = ((base + off + 127) & ~127) - base
+        off = start + nbytes
+        return img[start:start + nbytes]
+    take(4 * num_pixels)
+    take(4 * num_pixels)
+    return take(8 * num_pixels).view(torch.int32).reshape(num_pixels, 2)[:num_tiles]

@@ -51,3 +51,41 @@ def assert_images_close(a, b, atol=1e-4, outlier_frac=0.0, what=""):
     err = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
     frac = (err > atol).mean()
     assert frac <= outlier_frac, f"{what}: {frac:.2e} of pixels beyond {atol} (max {err.max():.3e})"
+
+
+def assert_binned_list_is_culled_reference_list(ex, ref_point_list, ref_ranges, W, H, P):
+    """The binning keeps a (Gaussian, tile) pair of the reference's rect only if the Gaussian can reach alpha >= 1/255 on
+    some pixel of the tile (exact tile culling).  So the sorted list must be the REFERENCE's sorted list with entries
+    removed -- same relative order -- and every removed entry must be provably inert: no pixel of its tile passes the
+    reference's own `power <= 0 && alpha >= 1/255` test (forward.cu:349-355).  Returns the number of removed entries.
+    ex: _C.debug_export dict; ref_point_list [R_ref], ref_ranges [>=T, 2]: the reference's (or the pinned oracle's)."""
+    dev = ex["point_list"].device
+    our_pl, our_rg = ex["point_list"].long(), ex["ranges"].long()
+    T = our_rg.shape[0]
+    ref_pl = torch.as_tensor(np.asarray(ref_point_list.cpu() if torch.is_tensor(ref_point_list) else ref_point_list).astype(np.int64)).to(dev)
+    ref_rg = torch.as_tensor(np.asarray(ref_ranges.cpu() if torch.is_tensor(ref_ranges) else ref_ranges).astype(np.int64)).to(dev).reshape(-1, 2)[:T]
+    tiles = torch.arange(T, device=dev)
+    ref_tile = torch.repeat_interleave(tiles, ref_rg[:, 1] - ref_rg[:, 0])
+    our_tile = torch.repeat_interleave(tiles, our_rg[:, 1] - our_rg[:, 0])
+    assert ref_tile.numel() == ref_pl.numel(), "reference ranges do not cover its list"
+    assert our_tile.numel() == our_pl.numel() == ex["num_binned"]
+    ref_key, our_key = ref_tile * P + ref_pl, our_tile * P + our_pl
+    kept = torch.isin(ref_key, our_key)
+    assert int(kept.sum()) == our_key.numel(), "binned an instance the reference does not have"
+    assert torch.equal(ref_key[kept], our_key), "binned list is not the reference's order"
+    dt, dg = ref_tile[~kept], ref_pl[~kept]
+    gx = (W + 15) // 16
+    px0, py0 = ((dt % gx) * 16).float(), ((dt // gx) * 16).float()
+    m2, co = ex["means2D"][dg], ex["conic_opacity"][dg]
+    off = torch.arange(16, device=dev, dtype=torch.float32)
+    step = 1 << 16
+    for c in range(0, dg.numel(), step):
+        sl = slice(c, c + step)
+        X, Y = px0[sl, None, None] + off[None, None, :], py0[sl, None, None] + off[None, :, None]
+        dx, dy = m2[sl, 0, None, None] - X, m2[sl, 1, None, None] - Y
+        A, B, C, o = (co[sl, i, None, None] for i in range(4))
+        power = -0.5 * (A * dx * dx + C * dy * dy) - B * dx * dy
+        alpha = torch.clamp(o * torch.exp(power), max=0.99)
+        live = (X < W) & (Y < H) & (power <= 0) & (alpha >= 1.0 / 255.0)
+        assert not bool(live.any()), "a culled (Gaussian, tile) pair could have contributed"
+    return int((~kept).sum())

@@ -137,7 +137,7 @@ def test_debug_mode_empty_input_and_side_stream():
     assert z.grad is not None and z.grad.shape == (0, 3)
 
 
-@pytest.mark.parametrize("P,min_n", [(9000, 4096), (24000, 12288), (40000, 26624)])
+@pytest.mark.parametrize("P,min_n", [(9000, 4096), (24000, 12288), (50000, 26624)])
 def test_large_tile_sort_paths(P, min_n):
     """Crowded tiles: more instances than the small sort kernel holds (-> the two-CTAs-per-SM tier), more than that
     tier holds (-> the one-CTA-per-SM tier) and more than fit in shared memory at all (-> global-memory path).
@@ -145,7 +145,7 @@ def test_large_tile_sort_paths(P, min_n):
     from gaustudio_b200 import _C
     from oracle.oracle import Oracle
     rng = np.random.RandomState(4)
-    W, H = 32, 32
+    W, H = 16, 16  # a single tile: every splat that can contribute at all lands in it
     cam = scenes.camera(W, H, 30.0, (3.0, 0.2, 0.1))
     xyz = (0.05 * rng.randn(P, 3)).astype(np.float32)
     sc = np.full((P, 3), 0.02, np.float32); rot = np.tile(np.array([1, 0, 0, 0], np.float32), (P, 1))
@@ -171,13 +171,13 @@ def test_large_tile_sort_paths(P, min_n):
     rg = ex["ranges"].long()
     tile_of = torch.repeat_interleave(torch.arange(rg.shape[0], device=dev), rg[:, 1] - rg[:, 0])
     assert bool(((key[1:] > key[:-1]) | (tile_of[1:] != tile_of[:-1])).all())
-    # ... and every tile holds exactly the oracle's set of Gaussians
+    # ... and every tile holds a subset of the oracle's Gaussians (the rest is culled as provably inert; the proof
+    # against the reference's own list is in test_gpu_parity / test_gpu_fullsize)
     ob = o.binning()
-    assert np.array_equal(ob["ranges"].astype(np.int64), rg.cpu().numpy())
-    got, want = ids.cpu().numpy(), ob["point_list"].astype(np.int64)
+    got, want, org = ids.cpu().numpy(), ob["point_list"].astype(np.int64), ob["ranges"].astype(np.int64)
     for t in range(rg.shape[0]):
         a, b_ = int(rg[t, 0]), int(rg[t, 1])
-        assert np.array_equal(np.sort(got[a:b_]), np.sort(want[a:b_]))
+        assert np.isin(got[a:b_], want[org[t, 0]:org[t, 1]]).all() and len(set(got[a:b_].tolist())) == b_ - a
     U.assert_images_close(color.cpu().numpy(), out["color"], atol=1e-4, outlier_frac=2e-3, what="color")
 
 
@@ -208,7 +208,8 @@ def test_equal_depth_ties_keep_index_order():
                         cam.camera_center.numpy(), math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), W, H, 0,
                         colors_precomp=col, scales=sc, rotations=rot)
         assert out["num_rendered"] == R and int((ex["ranges"][:, 1] - ex["ranges"][:, 0]).max()) > 256
-        assert np.array_equal(o.binning()["point_list"], ex["point_list"].cpu().numpy().astype(np.uint32))
+        ob = o.binning()
+        U.assert_binned_list_is_culled_reference_list(ex, ob["point_list"], ob["ranges"], W, H, P)
 
 
 def test_fused_activations_match_unfused():

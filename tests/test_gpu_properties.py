@@ -32,19 +32,24 @@ def test_full_size_binning_and_image_invariants(big):
     R, color, depth, median, opacity, radii, gb, bb, ib = _C.rasterize_gaussians(*a)
     P, W, H = c["P"], c["W"], c["H"]
     ex = _C.debug_export(P, W, H, R, gb, bb, ib)
+    # num_rendered keeps the reference's meaning (sum of the tile-rect areas); the binned list is shorter: pairs that
+    # cannot reach alpha >= 1/255 anywhere in the tile are culled (their inertness is proven in test_gpu_parity /
+    # test_gpu_fullsize against the reference's own list)
     assert R == int(ex["tiles_touched"].long().sum()) > 4_000_000
+    Rb = ex["num_binned"]
+    assert 0.4 * R < Rb < 0.95 * R
     rg = ex["ranges"].long()
     n = rg[:, 1] - rg[:, 0]
-    assert int(n.sum()) == R
+    assert int(n.sum()) == Rb
     nz = rg[n > 0]
-    assert int(nz[0, 0]) == 0 and int(nz[-1, 1]) == R and torch.equal(nz[1:, 0], nz[:-1, 1])
+    assert int(nz[0, 0]) == 0 and int(nz[-1, 1]) == Rb and torch.equal(nz[1:, 0], nz[:-1, 1])
     # per-tile order: ascending (depth bits, gaussian index) -- the reference's stable (tile|depth) sort
     ids = ex["point_list"].long()
     key = (ex["depths"].view(torch.int32).long()[ids] << 32) | ids
     tile_of = torch.repeat_interleave(torch.arange(rg.shape[0], device=dev), n)
     same = tile_of[1:] == tile_of[:-1]
     assert bool(((key[1:] > key[:-1]) | ~same).all())
-    assert torch.equal(torch.bincount(ids, minlength=P), ex["tiles_touched"].long())
+    assert bool((torch.bincount(ids, minlength=P) <= ex["tiles_touched"].long()).all())
     assert torch.equal(opacity[0], 1 - ex["final_T"])
     assert float(opacity.min()) >= 0 and float(opacity.max()) <= 1 and bool(torch.isfinite(color).all())
     # n_contrib never exceeds the tile's list length

@@ -137,9 +137,11 @@ def test_backward_is_the_gradient_of_forward_f64():
             assert abs(fd - an) <= 1e-5 * max(1.0, abs(fd), abs(an)), (k, idx, fd, an)
 
 
-def test_cull_bound_is_conservative():
-    """numpy restatement of may_touch() (gaustudio_b200/csrc/gsr_render.cu): the sub-tile test may only drop a
-    Gaussian if NO pixel of the 8x4 block passes the reference's alpha >= 1/255 test."""
+@pytest.mark.parametrize("bw,bh", [(8, 4), (16, 16)])
+def test_cull_bound_is_conservative(bw, bh):
+    """numpy restatement of may_touch() (gaustudio_b200/csrc/gsr_internal.cuh): the rectangle test -- 8x4 blocks in the
+    compositing kernels, whole 16x16 tiles in the binning -- may only drop a Gaussian if NO pixel of the rectangle passes
+    the reference's alpha >= 1/255 test."""
     rng = np.random.default_rng(3)
     n = 20000
     th = rng.uniform(0, np.pi, n); s1 = np.exp(rng.uniform(-1.0, 3.0, n)); s2 = np.exp(rng.uniform(-1.0, 3.0, n))
@@ -149,8 +151,8 @@ def test_cull_bound_is_conservative():
     A, B, C = (cov[:, 2] / det).astype(np.float32), (-cov[:, 1] / det).astype(np.float32), (cov[:, 0] / det).astype(np.float32)
     o = rng.uniform(0.001, 1.0, n).astype(np.float32)
     gx, gy = rng.uniform(-40, 48, n).astype(np.float32), rng.uniform(-40, 44, n).astype(np.float32)
-    rx0, ry0, rx1, ry1 = 0.0, 0.0, 7.0, 3.0
-    px, py = np.meshgrid(np.arange(8, dtype=np.float32), np.arange(4, dtype=np.float32))
+    rx0, ry0, rx1, ry1 = 0.0, 0.0, float(bw - 1), float(bh - 1)
+    px, py = np.meshgrid(np.arange(bw, dtype=np.float32), np.arange(bh, dtype=np.float32))
     dx = gx[:, None, None] - px[None]; dy = gy[:, None, None] - py[None]
     power = -0.5 * (A[:, None, None] * dx * dx + C[:, None, None] * dy * dy) - B[:, None, None] * dx * dy
     alpha = np.minimum(0.99, o[:, None, None] * np.exp(power))
