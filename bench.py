@@ -742,24 +742,50 @@ def run_train(a, _C, L, parallel, model, hcams, c, nviews_total, step, renderer,
         for p, g in zip(params, grads):
             p.grad = g
 
-    def view(cam):
+    def view_eager(cam, which):
         out = renderer.render(cam, model)
         loss = loss_fn(out)
         loss.backward()   # accumulates into the bound bucket's views
         normal(cam, out["rendered_depth"].detach()[0])
         return loss.detach()
 
+    # one CUDA graph per bucket: render + loss + backward (accumulating into that bucket's views) + depth->normal
+    graphs = None
+    if a.graph:
+        try:
+            from gaustudio_b200.graphs import GraphedViewStep
+            post = lambda cam, out: normal(hcams[0], out["rendered_depth"].detach()[0])  # noqa: E731
+            sample = [hc.upload(dev) for hc in hcams[:: max(1, len(hcams) // 6)]]
+            bind(gradsA)
+            gA = GraphedViewStep(renderer, model, loss_fn, sample, post_fn=post, accumulate=True)
+            graphs = [gA]
+            if V > 1:
+                bind(gradsB)
+                graphs.append(GraphedViewStep(renderer, model, loss_fn, sample[:1], capacity=gA.capacity, post_fn=post,
+                                              accumulate=True))
+            bucketA.zero()
+            if V > 1:
+                bucketB.zero()
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
+            graphs = None
+
+    def view(cam, which):
+        if graphs is None:
+            return view_eager(cam, which)
+        return graphs[which](PinnedCam(cam) if not hasattr(cam, "world_view_transform") else cam)
+
     def train_step(cams, comm=True):
         bind(gradsA)
         tot = 0.0
         for v in range(nA):
-            tot = tot + view(cams[v])
+            tot = tot + view(cams[v], 0)
         if comm:
             bucketA.all_reduce(async_op=True)
         if V > 1:
             bind(gradsB)
             for v in range(nA, V):
-                tot = tot + view(cams[v])
+                tot = tot + view(cams[v], 1)
             if comm:
                 bucketB.all_reduce(async_op=True)
         if comm:
@@ -815,6 +841,8 @@ def run_train(a, _C, L, parallel, model, hcams, c, nviews_total, step, renderer,
                                   f"; {V} views per rank per optimizer step, fused AdamW",
                       "global_batch_views": V * world, "parallelism": f"data-parallel x{world}",
                       "grad_bytes_per_all_reduce": int(bucketA.flat.numel() * 4)},
+           "launch": "one CUDA graph per view (gradients accumulate into the all-reduce buckets inside the graph)"
+                     if graphs is not None else "eager kernel launches",
            "ms_per_step_without_comm": res["no_comm"],
            "exposed_comm_ms": res["with_comm"] - res["no_comm"],
            "params_identical_across_ranks": ident}

@@ -349,12 +349,23 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
           if (tiles <= (uint32_t)kBigRect) {
             const CullRec cr = cull_prep(r0, r1, tau);
             tmask = 0;
-            int i = 0;
-            for (int ty = y0; ty < y1; ty++)
-              for (int tx = x0; tx < x1; tx++, i++)
+            // only the tiles that overlap the bounding box of the alpha >= 1/255 ellipse {A dx^2 + 2B dx dy + C dy^2 <= tau}
+            // (half extents sqrt(tau C / det), sqrt(tau A / det), slightly inflated) need the exact test
+            int sx0 = x0, sx1 = x1, sy0 = y0, sy1 = y1;
+            if (!cr.odd && tau >= 0.f) {
+              const float idet = 1.0f / (conA * conC - conB * conB);
+              const float hx = sqrtf(tau * conC * idet) * 1.001f + 0.01f, hy = sqrtf(tau * conA * idet) * 1.001f + 0.01f;
+              if (hx < 1e6f && hy < 1e6f) {  // also false for NaN
+                sx0 = max(x0, (int)floorf((px - hx) * (1.0f / TILE_X))); sx1 = min(x1, (int)floorf((px + hx) * (1.0f / TILE_X)) + 1);
+                sy0 = max(y0, (int)floorf((py - hy) * (1.0f / TILE_Y))); sy1 = min(y1, (int)floorf((py + hy) * (1.0f / TILE_Y)) + 1);
+              }
+            }
+            const int rw = x1 - x0;
+            for (int ty = sy0; ty < sy1; ty++)
+              for (int tx = sx0; tx < sx1; tx++)
                 if (may_touch(cr, (float)(tx * TILE_X), (float)(ty * TILE_Y), (float)min(tx * TILE_X + TILE_X - 1, a.W - 1),
                               (float)min(ty * TILE_Y + TILE_Y - 1, a.H - 1)))
-                  tmask |= 1u << i;
+                  tmask |= 1u << ((ty - y0) * rw + (tx - x0));
           }
         }
       }

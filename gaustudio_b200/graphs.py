@@ -41,6 +41,10 @@ class GraphedViewStep:
     `example_cameras` (rendered eagerly once each).  `step.max_rendered()` returns the largest count any replay
     needed -- compare it with `step.capacity` (an overflowing view is rendered incompletely, never out of bounds).
 
+    `accumulate=True` keeps the parameters' CURRENT `.grad` tensors (e.g. the views of a `parallel.GradBucket`) and
+    captures the in-place accumulation into them, so several replays sum their gradients into the same buffers -- the
+    caller zeroes them (the fused optimizer step does, `zero_grad=True`).  They are zeroed once after the capture.
+
     The fixed-capacity forward mode is only active during warm-up and capture: the caller's own forward mode
     (`_C.set_pipelined`) is restored before the constructor returns, so eager renders afterwards behave as before.
 
@@ -48,7 +52,8 @@ class GraphedViewStep:
     accumulator to the stream of its first backward, and a legacy-default-stream binding is illegal under capture
     (cudaErrorStreamCaptureImplicit).  Eager steps after the capture are fine."""
 
-    def __init__(self, renderer, model, loss_fn, example_cameras, capacity=None, post_fn=None, device=None):
+    def __init__(self, renderer, model, loss_fn, example_cameras, capacity=None, post_fn=None, device=None,
+                 accumulate=False):
         dev = device or model._xyz.device
         self.dev, self.model = dev, model
         cams = list(example_cameras)
@@ -79,19 +84,26 @@ class GraphedViewStep:
                 extra = post_fn(self.cam, out) if post_fn is not None else None
                 return loss.detach(), extra
 
+            if accumulate and any(p.grad is None for p in params):
+                raise ValueError("GraphedViewStep(accumulate=True): every parameter needs a .grad tensor to accumulate into")
             with torch.cuda.stream(side):
                 for _ in range(3):  # warm-up outside capture (allocator, lazy module loads)
-                    for p in params:
-                        p.grad = None
+                    if not accumulate:
+                        for p in params:
+                            p.grad = None
                     body()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
-            for p in params:
-                p.grad = None
+            if not accumulate:
+                for p in params:
+                    p.grad = None
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.loss, self.extra = body()
             self.grads = [p.grad for p in params]
+            if accumulate:
+                for g in self.grads:
+                    g.zero_()
             self.rmax = _C._pl().rmax  # device-side running max of num_rendered, updated inside the graph
             self.rmax.zero_()
         finally:
