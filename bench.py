@@ -775,26 +775,38 @@ def run_train(a, _C, L, parallel, model, hcams, c, nviews_total, step, renderer,
             return view_eager(cam, which)
         return graphs[which](PinnedCam(cam) if not hasattr(cam, "world_view_transform") else cam)
 
+    main_stream = torch.cuda.current_stream(dev)
+    sA, sB = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
     def train_step(cams, comm=True):
-        bind(gradsA)
-        tot = 0.0
-        for v in range(nA):
-            tot = tot + view(cams[v], 0)
-        if comm:
-            bucketA.all_reduce(async_op=True)
-        if V > 1:
-            bind(gradsB)
-            for v in range(nA, V):
-                tot = tot + view(cams[v], 1)
+        """The two halves of the step's views are independent (same parameters): they run on two streams, each followed by
+        its bucket's all_reduce; the optimizer step joins both."""
+        sA.wait_stream(main_stream)
+        sB.wait_stream(main_stream)
+        with torch.cuda.stream(sA):
+            bind(gradsA)
+            tot = 0.0
+            for v in range(nA):
+                tot = tot + view(cams[v], 0)
             if comm:
-                bucketB.all_reduce(async_op=True)
+                bucketA.all_reduce(async_op=True)
+        totB = 0.0
+        if V > 1:
+            with torch.cuda.stream(sB):
+                bind(gradsB)
+                for v in range(nA, V):
+                    totB = totB + view(cams[v], 1)
+                if comm:
+                    bucketB.all_reduce(async_op=True)
+        main_stream.wait_stream(sA)
+        main_stream.wait_stream(sB)
         if comm:
             bucketA.wait()
             if V > 1:
                 bucketB.wait()
         bind(gradsA)
         opt.step(grad_scale=scale, zero_grad=True, extra_grads=None if V == 1 else gradsB)
-        return tot / V
+        return (tot + totB) / V
 
     _C.set_pipelined(bool(a.pipelined))
     cams_of = lambda s: [hcams[(Wn + s * V + v) % len(hcams)] for v in range(V)]  # noqa: E731
@@ -803,9 +815,11 @@ def run_train(a, _C, L, parallel, model, hcams, c, nviews_total, step, renderer,
     for s in range(max(3, Wn // V)):
         train_step(cams_of(s))
     sync_all()
-    # timed: with communication, then the same steps without it (exposed communication = the difference)
+    # timed: with communication; then cross-rank parameter identity; then the same steps without communication
+    # (exposed communication = the difference; the ranks drift apart in that leg, so it comes last)
     res = {}
-    for label, comm in (("with_comm", True), ("no_comm", False)):
+
+    def timed(comm):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
         e0.record()
@@ -813,21 +827,16 @@ def run_train(a, _C, L, parallel, model, hcams, c, nviews_total, step, renderer,
             train_step(cams_of(s), comm=comm and world > 1)
         e1.record()
         sync_all()
-        res[label] = parallel.barrier_max_ms(e0.elapsed_time(e1), dev) / K
-    _C.check_pipeline(wait=True)
-    # cross-rank parameter identity after the synchronised steps (only the with_comm steps keep ranks identical, so
-    # re-synchronise: one more communicating step from identical parameters would not repair drift -> compare a
-    # checksum taken before the no_comm leg instead)
+        return parallel.barrier_max_ms(e0.elapsed_time(e1), dev) / K
+    res["with_comm"] = timed(True)
     ident = None
     if world > 1:
-        for p in params:
-            dist.broadcast(p.data, src=0)
-        for s in range(3):
-            train_step(cams_of(s), comm=True)
-        chk = torch.stack([p.detach().double().sum() for p in params])
+        chk = torch.stack([p.detach().double().sum() for p in params] + [p.detach().double().abs().sum() for p in params])
         allc = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         ident = bool(all(torch.equal(allc[0], x) for x in allc))
+    res["no_comm"] = timed(False)
+    _C.check_pipeline(wait=True)
     if rank != 0:
         if world > 1:
             dist.barrier()

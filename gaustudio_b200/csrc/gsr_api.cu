@@ -6,11 +6,13 @@
 #include <cmath>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
+#include <cuda.h>               // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved through the runtime)
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 
 namespace gsr {
@@ -80,6 +82,36 @@ const DeviceInfo& device_info() {
   }
   return d;
 }
+
+// ---- optional TMA gather4 staging of the compositing forward (GSR_FWD_TMA=1, read once per process) ----
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool fwd_tma_enabled() {
+  static const bool on = [] { const char* e = getenv("GSR_FWD_TMA"); return e && e[0] == '1'; }();
+  return on;
+}
+// 2-D view of the splat array for tile::gather4: rows = Gaussians, 12 floats (48 B) each; box = one row
+bool encode_splat_map(CUtensorMap* tm, const float4* splat, int P) {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {12, (cuuint64_t)P};
+  const cuuint64_t strides[1] = {SPLAT_BYTES};
+  const cuuint32_t box[2] = {12, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float4*>(splat), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
 
 GeomView carve_geom(char* base, int P) {
   GeomView g;
@@ -328,7 +360,9 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
     { Prof pf(3, st); launch_tile_sort(T, g, im, b, st); }
     if (!stage_ok(dbg, st, "tile_sort")) return -1;
   }
-  { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, g, out_color, out_depth, out_median_depth, out_opacity, st); }
+  CUtensorMap tmap;
+  const bool use_tma = fwd_tma_enabled() && encode_splat_map(&tmap, g.splat, P);
+  { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, g, use_tma ? &tmap : nullptr, out_color, out_depth, out_median_depth, out_opacity, st); }
   if (!stage_ok(dbg, st, "render_fwd")) return -1;
   return ret;
 }

@@ -99,8 +99,9 @@ void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStrea
 void launch_tile_scan(ImageView im, int T, cudaStream_t st);
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
-void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, float* out_color, float* out_depth,
-                       float* out_median, float* out_opacity, cudaStream_t st);
+// splat_tensor_map: a CUtensorMap over the [P][12 float] splat array (TMA gather4 staging) or nullptr (LDGSTS staging)
+void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, const void* splat_tensor_map,
+                       float* out_color, float* out_depth, float* out_median, float* out_opacity, cudaStream_t st);
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
                        const float* dL_dopacity, cudaStream_t st);

@@ -30,6 +30,8 @@
 //    n_contrib instead of the end of the list.
 #include "gsr_internal.cuh"
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time in gsr_api.cu)
 
 namespace gsr {
 
@@ -69,6 +71,41 @@ __device__ __forceinline__ void stage_gather(float4* dst, const float4* __restri
   }
   cp_async_arrive(full);
 }
+// ---- TMA tile::gather4 staging (opt-in, GSR_FWD_TMA=1) -----------------------------------------
+// One instruction fetches FOUR 48-byte records, given their row indices in the [P][12 float] splat array, into
+// 192 contiguous bytes of shared memory.  The destination of a tensor copy must be 128-byte aligned, so the staged
+// batch is laid out in 256-byte groups of four records (192 B used): record r sits at (r / 4) * 256 + (r % 4) * 48.
+constexpr int TMA_GROUP_F4 = 16;                                   // float4 per group of four records
+constexpr int TMA_STAGE_F4 = (RB / 4) * TMA_GROUP_F4;              // 8 KB per stage
+__device__ __forceinline__ void tma_gather4(void* dst_smem, const CUtensorMap* tm, int r0, int r1, int r2, int r3,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(smem_u32(dst_smem)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// producer warp, TMA flavour: lane l fetches records 4l .. 4l+3 of the batch with one gather4 (indices past the end of
+// the batch repeat the last valid one: the slots are never read)
+__device__ __forceinline__ void stage_gather_tma(float4* dst, const CUtensorMap* tm, const uint32_t* __restrict__ ids,
+                                                 int cnt, int lane, unsigned long long* full) {
+  const int r = 4 * lane;
+  if (r < cnt) {
+    const int last = cnt - 1;
+    const int i0 = (int)ids[r], i1 = (int)ids[min(r + 1, last)], i2 = (int)ids[min(r + 2, last)], i3 = (int)ids[min(r + 3, last)];
+    mbar_arrive_expect(full, 4 * SPLAT_BYTES);
+    tma_gather4(dst + lane * TMA_GROUP_F4, tm, i0, i1, i2, i3, full);
+  } else {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
+  }
+}
+template <bool TMA> __device__ __forceinline__ const float4* rec_at(const float4* sb, int j) {
+  return TMA ? sb + (j >> 2) * TMA_GROUP_F4 + (j & 3) * SPLAT_F4 : sb + j * SPLAT_F4;
+}
+
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -114,8 +151,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // Consumer warps never meet at a CTA-wide barrier inside the loop, so a block with little work does not
 // wait for a crowded one batch by batch.
 // ---------------------------------------------------------------------------------------------
-struct Ring {
-  float4 buf[NSTAGE][STAGE_F4];
+template <int STAGE>
+struct RingT {
+  float4 buf[NSTAGE][STAGE];
   unsigned long long full[NSTAGE];
   unsigned long long empty[NSTAGE];
   unsigned ndone;           // forward: consumer warps that have no live pixel left
@@ -123,7 +161,10 @@ struct Ring {
   unsigned maxc[NBLK];
 };
 
-__device__ __forceinline__ void ring_init(Ring& r, int consumers) {
+typedef RingT<STAGE_F4> Ring;
+
+template <int STAGE>
+__device__ __forceinline__ void ring_init(RingT<STAGE>& r, int consumers) {
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; s++) { mbar_init(&r.full[s], 32); mbar_init(&r.empty[s], consumers); }
@@ -139,13 +180,15 @@ __device__ __forceinline__ void ring_init(Ring& r, int consumers) {
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_THREADS = TILE_PIX + 32;
 
+template <bool TMA>
 __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx, ImageView im, BinView bin,
                                                             const float4* __restrict__ splat,
+                                                            const __grid_constant__ CUtensorMap tmap,
                                                             float* __restrict__ out_color,
                                                             float* __restrict__ out_depth,
                                                             float* __restrict__ out_median,
                                                             float* __restrict__ out_opacity) {
-  __shared__ __align__(128) Ring ring;
+  __shared__ __align__(128) RingT<TMA ? TMA_STAGE_F4 : STAGE_F4> ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
   const uint2 range = im.tile_range[tile];
@@ -166,7 +209,8 @@ __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx
         stop = *(volatile unsigned*)&ring.ndone == NBLK;  // every pixel of the tile is finished
       }
       if (__shfl_sync(FULL, stop, 0)) break;
-      stage_gather(ring.buf[s], splat, ids + b * RB, min(RB, n - b * RB), lane, &ring.full[s]);
+      if (TMA) stage_gather_tma(ring.buf[s], &tmap, ids + b * RB, min(RB, n - b * RB), lane, &ring.full[s]);
+      else stage_gather(ring.buf[s], splat, ids + b * RB, min(RB, n - b * RB), lane, &ring.full[s]);
       issued = b + 1;
     }
     // every copy must have landed before the CTA's shared memory is released
@@ -212,15 +256,15 @@ __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx
       const int j = base + lane;
       bool keep = false;
       if (j < cnt) {
-        const float4 c0 = sb[j * SPLAT_F4], c1 = sb[j * SPLAT_F4 + 1];
-        keep = may_touch(cull_prep(c0, c1, sb[j * SPLAT_F4 + 2].w), rx0, ry0, rx1, ry1);
+        const float4* cr = rec_at<TMA>(sb, j);
+        keep = may_touch(cull_prep(cr[0], cr[1], cr[2].w), rx0, ry0, rx1, ry1);
       }
       unsigned mask = __ballot_sync(FULL, keep);
       const unsigned pos0 = (unsigned)(b * RB + base + 1);
       while (mask) {
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
-        const float4* rec = sb + (base + bit) * SPLAT_F4;
+        const float4* rec = rec_at<TMA>(sb, base + bit);
         const float4 q0 = rec[0], q1 = rec[1];
         // forward.cu:343-356 with the contraction of the reference SASS
         const float dx = q0.x - pxf, dy = q0.y - pyf;
@@ -470,9 +514,18 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
 
 }  // namespace
 
-void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, float* out_color,
-                       float* out_depth, float* out_median, float* out_opacity, cudaStream_t st) {
-  k_render_fwd<<<gx * gy, FWD_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, out_color, out_depth, out_median, out_opacity);
+void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, const void* splat_tensor_map,
+                       float* out_color, float* out_depth, float* out_median, float* out_opacity, cudaStream_t st) {
+  if (splat_tensor_map) {
+    k_render_fwd<true><<<gx * gy, FWD_THREADS, 0, st>>>(W, H, gx, im, b, g.splat,
+                                                        *static_cast<const CUtensorMap*>(splat_tensor_map), out_color,
+                                                        out_depth, out_median, out_opacity);
+  } else {
+    CUtensorMap none;
+    memset(&none, 0, sizeof(none));
+    k_render_fwd<false><<<gx * gy, FWD_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, none, out_color, out_depth, out_median,
+                                                         out_opacity);
+  }
 }
 
 // Pixels per lane of the compositing backward (1, 2, 4 or 8) and the occupancy the kernel is compiled for
