@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsr_b200.so")
+# GSR_LIB selects another build of the same sources (the ring-stress variant of the tests); default: the in-tree library
+LIB_PATH = os.environ.get("GSR_LIB") or os.path.join(_HERE, "libgsr_b200.so")
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64

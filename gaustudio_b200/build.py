@@ -51,5 +51,32 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+STRESS_LIB = os.path.join(HERE, "libgsr_b200_stress.so")
+
+
+def build_stress_variant(force=False):
+    """Same sources with the compositing ring shrunk to ONE stage of 32 records (-DGSR_NSTAGE=1 -DGSR_RB=32): test
+    infrastructure for tests/test_gpu_ring_stress.py (selected with GSR_LIB=<path>); never loaded by default."""
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    if not force and os.path.exists(STRESS_LIB) and all(os.path.getmtime(STRESS_LIB) >= os.path.getmtime(d) for d in deps):
+        return STRESS_LIB
+    objs, procs = [], []
+    for s in SOURCES:
+        o = os.path.join(CSRC, s.replace(".cu", ".stress.o"))
+        objs.append(o)
+        flags = [f for f in FLAGS if f not in ("-Xptxas", "-v")] + ["-DGSR_NSTAGE=1", "-DGSR_RB=32"]
+        procs.append((s, subprocess.Popen([NVCC, *flags, "-c", os.path.join(CSRC, s), "-o", o], stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True)))
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {s} (stress variant)")
+    subprocess.check_call([NVCC, "-shared", "-Xlinker", "-soname=libgsr_b200_stress.so", "-o", STRESS_LIB, *objs, "-lcudart", "-ldl"])
+    for o in objs:
+        os.remove(o)
+    return STRESS_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="-f" in sys.argv, verbose=True))

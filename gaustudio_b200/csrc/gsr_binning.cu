@@ -109,11 +109,11 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   unsigned depth_bits = 0, mask = 0;
   if (idx < P) {
-    // the three loads are issued together (the depth of a culled Gaussian is read but never used)
     const uint2 rc = g.rect[idx];
     mask = g.tile_mask[idx];
-    depth_bits = __float_as_uint(reinterpret_cast<const float*>(g.splat + (size_t)idx * SPLAT_F4 + 1)[2]);
     unpack_rect(rc, x0, y0, x1, y1);
+    // (the record of a culled Gaussian is never written: do not touch it)
+    if (x1 > x0) depth_bits = __float_as_uint(reinterpret_cast<const float*>(g.splat + (size_t)idx * SPLAT_F4 + 1)[2]);
   }
   const int w = x1 - x0, n = w * (y1 - y0);
   const unsigned lane = threadIdx.x & 31;

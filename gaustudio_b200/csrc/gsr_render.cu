@@ -37,8 +37,17 @@ namespace gsr {
 
 namespace {
 
-constexpr int RB = 128;                       // records per pipeline stage
-constexpr int NSTAGE = 4;                     // ring depth: consumer warps may drift this many batches apart
+// GSR_RB / GSR_NSTAGE: overridden only by the stress build of tests/test_gpu_ring_stress.py (1 stage of 32 records: every
+// batch is a wrap-around of the ring, so a protocol slip shows up as wrong pixels instead of hiding behind slack)
+#ifndef GSR_RB
+#define GSR_RB 128
+#endif
+#ifndef GSR_NSTAGE
+#define GSR_NSTAGE 4
+#endif
+constexpr int RB = GSR_RB;                    // records per pipeline stage (a multiple of 32)
+constexpr int NSTAGE = GSR_NSTAGE;            // ring depth: consumer warps may drift this many batches apart
+static_assert(RB % 32 == 0 && RB >= 32 && NSTAGE >= 1, "ring geometry");
 constexpr int STAGE_F4 = RB * SPLAT_F4;       // float4 per stage (6 KB)
 constexpr int NBLK = TILE_PIX / 32;           // 8 blocks of 8x4 pixels per tile
 constexpr unsigned FULL = 0xffffffffu;

@@ -83,3 +83,34 @@ def test_surface_point_cloud_ply(tmp_path):
     assert np.array_equal(np.stack([v["red"], v["green"], v["blue"]], 1), (rgb.astype(np.float64) * 255).astype(np.uint8))
     io.export_points_ply(str(p), xyz)  # positions only
     assert io.read_ply_vertices(str(p)).dtype.names == ("x", "y", "z")
+
+
+def test_ply_written_by_the_reference_exporter():
+    """tests/golden/ref_export.ply was produced by the reference's own `VanillaPointCloud.export` (executed unmodified,
+    tests/golden/make_golden_ply.py); `loaded_*` is what the reference's own `BasePointCloud.load` reads back from it.
+    Our loader must hold the same tensors, and our exporter must write the same bytes for the same in-memory model."""
+    import os
+    import tempfile
+    import numpy as np
+    import torch
+    from gaustudio_b200 import io as gio
+    from gaustudio_b200.synthetic import GaussianPointCloud
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ply, G = os.path.join(here, "ref_export.ply"), np.load(os.path.join(here, "ref_export_attrs.npz"))
+    m = gio.load_ply(ply)
+    for k in ("xyz", "opacity", "scale", "rot", "f_dc", "f_rest"):
+        ours = getattr(m, "_" + k).numpy()
+        assert np.array_equal(ours.reshape(G["loaded_" + k].shape), G["loaded_" + k]), k
+    # the SH tensor the rasterizer consumes, built exactly as the reference model builds it from what it loaded
+    # (vanilla_sg.py:102-106: reshape(P, -1, 3) of the loaded [P,3] / [P,45] arrays)
+    P = G["xyz"].shape[0]
+    want = np.concatenate([G["loaded_f_dc"].reshape(P, -1, 3), G["loaded_f_rest"].reshape(P, -1, 3)], axis=1)
+    assert np.array_equal(m.get_features.numpy(), want)
+    # our exporter on the in-memory model the reference exported (export o load is not the identity in the reference:
+    # SH goes out channel-major and comes back un-transposed, vanilla_sg.py:102-106 vs :147-148)
+    t = lambda k: torch.from_numpy(G[k])
+    src = GaussianPointCloud(t("xyz"), t("scale"), t("rot"), t("opacity"), t("f_dc"), t("f_rest"))
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.ply")
+        gio.export_ply(src, out)
+        assert open(out, "rb").read() == open(ply, "rb").read()
