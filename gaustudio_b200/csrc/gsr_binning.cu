@@ -35,7 +35,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_TPT = 8;
 constexpr int SCAN_TILES = SCAN_THREADS * SCAN_TPT;
-constexpr int SORT_CAP_SMALL_ = 4096;  // == SORT_CAP_SMALL below
+constexpr int SORT_CAP_SMALL_ = 6144;  // == SORT_CAP_SMALL below
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T) {
   __shared__ unsigned total[SCAN_TILES];  // tile totals, then their exclusive prefix within the round
   __shared__ unsigned warp_sums[32];
@@ -173,8 +173,9 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 // almost all of the SM's shared memory for the most crowded ones; only tiles beyond SORT_CAP_BIG entries fall back
 // to sorting in global memory (L2-resident scratch).  The two crowded tiers take their tiles from the compact list
 // the scan produced through an atomic ticket, so a CTA that drew a 25k-entry tile does not hold up a queue of others.
-constexpr int SORT_CAP_SMALL = 4096;   // 32 KB
+constexpr int SORT_CAP_SMALL = 6144;   // 48 KB: four CTAs per SM
 constexpr int SORT_CAP_MID = 12288;    // 96 KB: two CTAs per SM
+static_assert(SORT_CAP_SMALL == SORT_CAP_SMALL_, "scan and sort disagree on the small-tier capacity");
 constexpr int SORT_CAP_BIG = 26624;    // 208 KB (+ 16 KB of bucket counters)
 typedef unsigned long long u64;
 
@@ -361,6 +362,7 @@ void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t s
   constexpr int smem_small = SORT_CAP_SMALL * 8, smem_mid = SORT_CAP_MID * 8, smem_big = SORT_CAP_BIG * 8;
   const DeviceInfo& di = device_info();
   if (!di.sort_attr_set) {  // once per device
+    cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
     cudaFuncSetAttribute(mid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mid);
     cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
     di.sort_attr_set = true;

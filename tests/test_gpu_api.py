@@ -137,7 +137,7 @@ def test_debug_mode_empty_input_and_side_stream():
     assert z.grad is not None and z.grad.shape == (0, 3)
 
 
-@pytest.mark.parametrize("P,min_n", [(9000, 4096), (24000, 12288), (50000, 26624)])
+@pytest.mark.parametrize("P,min_n", [(9000, 4096), (12500, 6144), (24000, 12288), (50000, 26624)])
 def test_large_tile_sort_paths(P, min_n):
     """Crowded tiles: more instances than the small sort kernel holds (-> the two-CTAs-per-SM tier), more than that
     tier holds (-> the one-CTA-per-SM tier) and more than fit in shared memory at all (-> global-memory path).
