@@ -221,7 +221,7 @@ __device__ __forceinline__ void warp_sort_mem(u64* k, unsigned m, unsigned lane)
 template <int NB> struct SortShared {
   unsigned cnt[NB];        // bucket sizes, then running cursors of the split
   unsigned start[NB + 1];  // exclusive prefix of the bucket sizes
-  unsigned wsum[SORT_WARPS];
+  alignas(16) unsigned wsum[SORT_WARPS];  // own 16-byte slots: the compiler reads them with vector loads
   unsigned dmin, dmax;
 };
 

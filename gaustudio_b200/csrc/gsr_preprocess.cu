@@ -195,10 +195,51 @@ __device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, ui
   }
 }
 
+// Which tiles of a Gaussian's rect [x0,x1) x [y0,y1) (<= 32 tiles) can it contribute to at all?  Bit i (row-major in the
+// rect) is set iff some point of tile i's pixel box lies in the ellipse E = {q(d) <= tau'}, q(d) = A dx^2 + 2B dx dy + C dy^2,
+// d = pixel - mean, tau' = tau + margin (tau = 2 ln(255 o): alpha >= 1/255 needs q <= tau; the margin is the one of
+// may_touch, taken over the whole rect).  Row by row instead of tile by tile: within the band dy in [lo, hi] of a tile
+// row the ellipse spans dx in [xmin, xmax]; xmax(dy) = -(B/A) dy + sqrt((tau' - D dy^2) / A), D = C - B^2/A, is concave
+// with its maximum hx = sqrt(tau' C / det) at dy = -B hx / C (and xmin mirrors it), so both follow from one clamped
+// evaluation each, and the row's tiles are the contiguous run that overlaps [xmin, xmax] (convexity).  A superset of the
+// contributing tiles is always safe: the compositing kernels apply the reference's per-pixel test.
+__device__ __forceinline__ uint32_t tile_mask_of(float px, float py, float A, float B, float C, float opac, float tau,
+                                                 int x0, int y0, int x1, int y1, int W, int H) {
+  const int rw = x1 - x0;
+  const uint32_t all = (rw * (y1 - y0) >= 32) ? 0xffffffffu : ((1u << (rw * (y1 - y0))) - 1u);
+  if (opac < 0.0039f) return 0u;  // alpha <= o < 1/255 everywhere
+  const float det = A * C - B * B;
+  if (!(A > 1e-30f && C > 1e-30f && det > 0.f && A < 1e30f && C < 1e30f && tau >= 0.f)) return all;  // keep everything
+  // rounding margin of the per-pixel evaluation (may_touch): relative to the largest term over the rect + absolute
+  const float mx = fmaxf(fabsf(px - (float)(x0 * TILE_X)), fabsf((float)(x1 * TILE_X) - px));
+  const float my = fmaxf(fabsf(py - (float)(y0 * TILE_Y)), fabsf((float)(y1 * TILE_Y) - py));
+  const float taum = tau + 1e-5f * (A * mx * mx + C * my * my + 2.f * fabsf(B) * mx * my) + 1e-3f;
+  const float idet = 1.0f / det, iA = 1.0f / A;
+  const float hx = sqrtf(taum * C * idet), hy = sqrtf(taum * A * idet);
+  if (!(hx < 1e6f && hy < 1e6f)) return all;
+  const float dyx = -B * hx / C;  // dy of the ellipse's right-most point (the left-most one is at -dyx)
+  const float D = det * iA, BA = B * iA;
+  uint32_t mask = 0;
+  for (int ty = y0; ty < y1; ty++) {
+    const float lo = fmaxf((float)(ty * TILE_Y) - py, -hy), hi = fminf((float)min(ty * TILE_Y + TILE_Y - 1, H - 1) - py, hy);
+    if (lo > hi) continue;  // the row's band misses the ellipse
+    const float da = fminf(fmaxf(dyx, lo), hi), db = fminf(fmaxf(-dyx, lo), hi);
+    const float xmax = -BA * da + sqrtf(fmaxf(0.f, (taum - D * da * da) * iA)) * 1.0001f + 0.01f;
+    const float xmin = -BA * db - sqrtf(fmaxf(0.f, (taum - D * db * db) * iA)) * 1.0001f - 0.01f;
+    // tiles whose pixel columns [16 tx, 16 tx + 15] meet [px + xmin, px + xmax]
+    const int ta = max(x0, (int)ceilf((px + xmin - (float)(TILE_X - 1)) * (1.0f / TILE_X)));
+    const int tb = min(x1 - 1, (int)floorf((px + xmax) * (1.0f / TILE_X)));
+    if (ta > tb) continue;
+    const int first = (ty - y0) * rw + (ta - x0), len = tb - ta + 1;
+    mask |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << first;
+  }
+  return mask & all;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: forward.cu:155-256
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
+__global__ void __launch_bounds__(PRE_THREADS, 4) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
   extern __shared__ __align__(128) float sh_stage[];  // [256][3] f_dc rows, then [256][(M-1)*3] f_rest rows
   __shared__ __align__(8) unsigned long long sh_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,27 +387,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomV
           // Exact tile culling: a (Gaussian, tile) pair of the reference's rect is binned only if the Gaussian can
           // reach alpha >= 1/255 on some pixel of that tile.  For every other pair the reference `continue`s on all
           // 256 pixels (forward.cu:353-355), so dropping it changes no output -- only the internal lists get shorter.
-          if (tiles <= (uint32_t)kBigRect) {
-            const CullRec cr = cull_prep(r0, r1, tau);
-            tmask = 0;
-            // only the tiles that overlap the bounding box of the alpha >= 1/255 ellipse {A dx^2 + 2B dx dy + C dy^2 <= tau}
-            // (half extents sqrt(tau C / det), sqrt(tau A / det), slightly inflated) need the exact test
-            int sx0 = x0, sx1 = x1, sy0 = y0, sy1 = y1;
-            if (!cr.odd && tau >= 0.f) {
-              const float idet = 1.0f / (conA * conC - conB * conB);
-              const float hx = sqrtf(tau * conC * idet) * 1.001f + 0.01f, hy = sqrtf(tau * conA * idet) * 1.001f + 0.01f;
-              if (hx < 1e6f && hy < 1e6f) {  // also false for NaN
-                sx0 = max(x0, (int)floorf((px - hx) * (1.0f / TILE_X))); sx1 = min(x1, (int)floorf((px + hx) * (1.0f / TILE_X)) + 1);
-                sy0 = max(y0, (int)floorf((py - hy) * (1.0f / TILE_Y))); sy1 = min(y1, (int)floorf((py + hy) * (1.0f / TILE_Y)) + 1);
-              }
-            }
-            const int rw = x1 - x0;
-            for (int ty = sy0; ty < sy1; ty++)
-              for (int tx = sx0; tx < sx1; tx++)
-                if (may_touch(cr, (float)(tx * TILE_X), (float)(ty * TILE_Y), (float)min(tx * TILE_X + TILE_X - 1, a.W - 1),
-                              (float)min(ty * TILE_Y + TILE_Y - 1, a.H - 1)))
-                  tmask |= 1u << ((ty - y0) * rw + (tx - x0));
-          }
+          if (tiles <= (uint32_t)kBigRect) tmask = tile_mask_of(px, py, conA, conB, conC, opac, tau, x0, y0, x1, y1, a.W, a.H);
         }
       }
     }

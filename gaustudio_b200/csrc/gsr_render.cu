@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx
 // backward: 8 / NSUB consumer warps, each owning NSUB 8x4 blocks (lane = one pixel in every block), + producer
 // ---------------------------------------------------------------------------------------------
 // block s of warp w sits at (kx, ky) in units of (8, 4) pixels; regions are as square as possible:
-//   NSUB 1: 8x4    NSUB 2: 8x8    NSUB 4: 16x8    NSUB 8: the whole 16x16 tile
+//   NSUB 1: 8x4    NSUB 2: 8x8    (4: 16x8 and 8: the whole tile were measured too and are not instantiated)
 template <int NSUB> __device__ __forceinline__ int blk_kx(int w, int s) { return NSUB <= 2 ? (w & 1) : (s & 1); }
 template <int NSUB> __device__ __forceinline__ int blk_ky(int w, int s) {
   return NSUB == 1 ? (w >> 1) : NSUB == 2 ? (w >> 1) * 2 + s : NSUB == 4 ? w * 2 + (s >> 1) : (s >> 1);
@@ -537,14 +537,14 @@ void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, Ge
   }
 }
 
-// Pixels per lane of the compositing backward (1, 2, 4 or 8) and the occupancy the kernel is compiled for
-// (GSR_BWD_NSUB / GSR_BWD_MINB override the defaults, read once per process).
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+// Pixels per lane of the compositing backward: 1 (default) or 2 (GSR_BWD_NSUB=2, read once per process).  The A/B on
+// cfg 3 (profiles/r2_ab_bwd_variants.json: 1, 2, 4 and 8 pixels per lane, two occupancy targets each) has one pixel
+// per lane fastest -- fewer reductions per Gaussian do not make up for the resident warps the extra registers cost --
+// so only the two-pixel variant is kept as a validated alternative (tests/test_gpu_ring_stress.py).
+static int bwd_nsub() {
+  static const int v = [] { const char* e = getenv("GSR_BWD_NSUB"); return (e && e[0] == '2') ? 2 : 1; }();
+  return v;
 }
-static int bwd_nsub() { static const int v = env_int("GSR_BWD_NSUB", 1); return v; }
-static int bwd_minb() { static const int v = env_int("GSR_BWD_MINB", 0); return v; }
 
 template <int NSUB, int MINB>
 static void launch_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
@@ -557,13 +557,8 @@ static void launch_bwd(int W, int H, int gx, int gy, const float* bg, ImageView 
 void launch_render_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian,
                        const float* dL_dopacity, cudaStream_t st) {
-#define GSR_BWD(N, M) launch_bwd<N, M>(W, H, gx, gy, bg, im, b, g, dL_dpix, dL_ddepth, dL_dmedian, dL_dopacity, st)
-  const int n = bwd_nsub(), mb = bwd_minb();
-  if (n == 2) { if (mb == 5) GSR_BWD(2, 5); else GSR_BWD(2, 4); }
-  else if (n == 4) { if (mb == 6) GSR_BWD(4, 6); else GSR_BWD(4, 5); }
-  else if (n == 8) GSR_BWD(8, 6);
-  else { if (mb == 5) GSR_BWD(1, 5); else GSR_BWD(1, 4); }
-#undef GSR_BWD
+  if (bwd_nsub() == 2) launch_bwd<2, 4>(W, H, gx, gy, bg, im, b, g, dL_dpix, dL_ddepth, dL_dmedian, dL_dopacity, st);
+  else launch_bwd<1, 4>(W, H, gx, gy, bg, im, b, g, dL_dpix, dL_ddepth, dL_dmedian, dL_dopacity, st);
 }
 
 }  // namespace gsr

@@ -31,7 +31,7 @@ for fused in (False, True):
         loss = sum((o[n] * torch.randn(o[n].shape, generator=g).to(dev)).sum() for n in ("render", "rendered_depth", "rendered_final_opacity"))
         loss.backward()
         key = f"{int(fused)}{k}"
-        out["img" + key] = hashlib.sha1(torch.cat([o[n].flatten() for n in ("render", "rendered_depth", "rendered_median_depth", "rendered_final_opacity")]).cpu().numpy().tobytes()).hexdigest()
+        out["img" + key] = hashlib.sha1(torch.cat([o[n].detach().flatten() for n in ("render", "rendered_depth", "rendered_median_depth", "rendered_final_opacity")]).cpu().numpy().tobytes()).hexdigest()
         out["grad" + key] = [float(p.grad.double().abs().sum()) for p in model.parameters_list()]
 print("RESULT" + json.dumps(out))
 '''
@@ -40,6 +40,7 @@ print("RESULT" + json.dumps(out))
 def _run(lib, **extra):
     env = dict(os.environ)
     env.pop("GSR_FWD_TMA", None)
+    env.pop("GSR_BWD_NSUB", None)
     if lib:
         env["GSR_LIB"] = lib
     else:
@@ -74,3 +75,9 @@ def test_tma_gather4_staging_reproduces_default_build():
     _same(ref, _run(None, GSR_FWD_TMA="1"), "with TMA gather4 staging")
     if os.path.exists(STRESS):
         _same(ref, _run(STRESS, GSR_FWD_TMA="1"), "with TMA gather4 staging on the one-stage ring")
+
+
+def test_two_pixels_per_lane_backward_matches_default():
+    """GSR_BWD_NSUB=2: every lane owns two pixels (8x8 region per warp) and sums a Gaussian's gradient over both before the
+    warp reduction.  Same forward, same gradients up to the order of the float reductions."""
+    _same(_run(None), _run(None, GSR_BWD_NSUB="2"), "with two pixels per lane in the backward")

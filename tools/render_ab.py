@@ -1,8 +1,10 @@
-"""A/B of the compositing-backward variants (GSR_BWD_NSUB = pixels per lane, GSR_BWD_MINB = occupancy the kernel is
-compiled for; both read once per process, so every variant runs in its own subprocess).  For each variant: forward
+"""A/B of the compositing-kernel variants selected by environment variables read once per process (GSR_BWD_NSUB = pixels
+per lane of the backward: 1 or 2; GSR_FWD_TMA=1 = TMA gather4 staging in the forward), one subprocess per variant.
+(Up to commit a9bd034 the backward also had 4 / 8 pixels per lane and a second occupancy target per variant --
+`GSR_BWD_MINB`; those measurements are in profiles/r2_ab_bwd_variants.json.)  For each variant: forward
 outputs must be BIT-IDENTICAL to the unmodified reference extension (oracle/_ref) and the gradients within 1e-3
 relative of the reference's, then per-kernel CUDA-event times over a few views.
-Usage: python tools/render_ab.py [cfg3] ["1 2:4 2:5 4:5 4:6 8"]"""
+Usage: python tools/render_ab.py [cfg3] ["1 2"]"""
 import json, os, subprocess, sys, tempfile
 
 CHILD = r'''
@@ -54,7 +56,7 @@ json.dump(res, open(out, "w"))
 '''
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
-variants = (sys.argv[2] if len(sys.argv) > 2 else "1 2:4 2:5 4:5 4:6 8").split()
+variants = (sys.argv[2] if len(sys.argv) > 2 else "1 2").split()
 rep = {"config": name, "variants": {}}
 with tempfile.TemporaryDirectory() as d:
     for v in variants:
