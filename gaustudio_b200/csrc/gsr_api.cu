@@ -144,12 +144,13 @@ ImageView carve_image(char* base, int W, int H) {
   take(p, im.tile_cursor, T * SUBBINS);
   take(p, im.tile_maxc, T);
   take(p, im.big_tiles, T);
+  take(p, im.tile_order, T);
   return im;
 }
 size_t image_bytes(int W, int H) {
   ImageView im = carve_image(nullptr, W, H);
   const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
-  return reinterpret_cast<size_t>(im.big_tiles + T) + 512;
+  return reinterpret_cast<size_t>(im.tile_order + T) + 512;
 }
 // The binning arrays are laid out for the instance count rounded up to 1 Mi entries: the buffer size (and with
 // it the caller's allocator block) then takes only a few distinct values across views instead of one per view.

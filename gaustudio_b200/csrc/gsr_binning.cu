@@ -101,6 +101,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T)
     im.hdr->num_rendered = carry;
     im.hdr->overflow = carry > cap ? 1u : 0u;
   }
+  // Longest-first launch order for the one-CTA-per-tile kernels (sort, compositing): a counting sort of the tiles into
+  // 64 size classes, heaviest class first.  Within a class the order is whatever the atomics give -- it only decides
+  // which CTA index works on which tile, never a result.
+  __shared__ unsigned cls_count[64], cls_start[64];
+  if (tid < 64) cls_count[tid] = 0;
+  __syncthreads();  // also makes this CTA's tile_range writes visible to itself
+  auto size_class = [&](int t) {
+    const uint2 r = im.tile_range[t];
+    return 63u - min(63u, (r.y - r.x) >> 6);  // class 0: >= 4032 instances ... class 63: < 64 (incl. empty)
+  };
+  for (int t = tid; t < T; t += SCAN_THREADS) atomicAdd(&cls_count[size_class(t)], 1u);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned run = 0;
+    for (int c = 0; c < 64; c++) { cls_start[c] = run; run += cls_count[c]; }
+  }
+  __syncthreads();
+  for (int t = tid; t < T; t += SCAN_THREADS) im.tile_order[atomicAdd(&cls_start[size_class(t)], 1u)] = (uint32_t)t;
 }
 
 // ---- level 1b: scatter one entry per (Gaussian, touched tile) ------------------------------------
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     work = sh_work;
   }
   if (work >= num_work) break;
-  const unsigned tile = MIN_N == 0 ? work : im.big_tiles[work];
+  const unsigned tile = MIN_N == 0 ? im.tile_order[work] : im.big_tiles[work];
   const uint2 range = im.tile_range[tile];
   const unsigned n = range.y - range.x;
   if (n <= (unsigned)MIN_N || (MAX_N != 0 && n > (unsigned)MAX_N)) continue;  // another launch owns this tile

@@ -57,6 +57,8 @@ struct ImageView {
   uint32_t* tile_cursor;  // [SUBBINS][T] write cursors of the scatter pass
   uint32_t* tile_maxc;    // [T] max n_contrib over the tile's pixels (bounds the backward traversal)
   uint32_t* big_tiles;    // [T] compact list of crowded tiles (hdr->num_big entries), built by the scan
+  uint32_t* tile_order;   // [T] tiles by decreasing instance count (64 size classes): CTA i of the per-tile kernels
+                          //     takes tile_order[i], so the long tiles start first and the short ones fill the tail
 };
 struct BinView {               // point_list comes FIRST: its address does not depend on the capacity (backward, export)
   uint32_t* point_list;       // [cap] Gaussian index per sorted tile instance (== BinningState::point_list)

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_render_fwd(int W, int H, int gx
                                                             float* __restrict__ out_opacity) {
   __shared__ __align__(128) RingT<TMA ? TMA_STAGE_F4 : STAGE_F4> ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
+  const int tile = (int)im.tile_order[blockIdx.x], tx = tile % gx, ty = tile / gx;  // longest tiles first
   const uint2 range = im.tile_range[tile];
   const int n = (int)(range.y - range.x);
   const int nb = (n + RB - 1) / RB;
@@ -354,7 +354,7 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
   constexpr int NCONS = NBLK / NSUB;
   __shared__ __align__(128) Ring ring;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, tx = tile % gx, ty = tile / gx;
+  const int tile = (int)im.tile_order[blockIdx.x], tx = tile % gx, ty = tile / gx;  // longest tiles first
   const uint2 range = im.tile_range[tile];
   const int nmax = (int)min(im.tile_maxc[tile], range.y - range.x);
   if (nmax == 0) return;
