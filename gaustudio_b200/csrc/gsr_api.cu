@@ -123,7 +123,6 @@ GeomView carve_geom(char* base, int P) {
   take(p, g.radii, (size_t)P);
   take(p, g.tiles_touched, (size_t)P);
   take(p, g.tile_mask, (size_t)P);
-  take(p, g.tile_rank, (size_t)P * RANK_SLOTS);
   take(p, g.grad, (size_t)P * GRAD_F);
   return g;
 }

@@ -139,37 +139,15 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
   // cursors of tiles that were dropped for capacity start at DROPPED, so their slots fail the range test
   const unsigned long long cap = im.hdr->capacity;
   const unsigned limit = cap < 0x80000000ull ? (unsigned)cap : 0x80000000u;
-  unsigned* shared_cur = im.tile_cursor + subbin_of(0, false) * T;  // sub-bin of the un-ranked instances
   auto put = [&](int tile, unsigned dbits, int gidx) {
-    const unsigned slot = atomicAdd(shared_cur + tile, 1u);
+    const unsigned slot = atomicAdd(&im.tile_cursor[subbin_of(gidx) * T + tile], 1u);
     if (slot < limit) b.ents[slot] = ((unsigned long long)dbits << 32) | (unsigned)gidx;
   };
-  const unsigned long long key = ((unsigned long long)depth_bits << 32) | (unsigned)idx;
-  if (is_ranked(n, mask)) {
-    // the projection kernel kept the rank of every instance: slot = start of the (tile, sub-bin) segment + rank,
-    // plain loads and stores, no atomics
-    const unsigned* base = im.tile_cursor + subbin_of(idx, true) * T;
-    const uint4* rp = reinterpret_cast<const uint4*>(g.tile_rank + (size_t)idx * RANK_SLOTS);
-    const uint4 ra = rp[0];
-    uint4 rb = make_uint4(0u, 0u, 0u, 0u);
-    if (__popc(mask) > 4) rb = rp[1];
-    const unsigned rk[RANK_SLOTS] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    unsigned slot[RANK_SLOTS];
-#pragma unroll
-    for (int k = 0; k < RANK_SLOTS; k++) {
-      slot[k] = 0xffffffffu;
-      if (mask) {
-        const int i = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const unsigned s0 = base[(y0 + i / w) * gx + x0 + i % w];  // 0x80000000 for a tile dropped for capacity
-        slot[k] = s0 + rk[k];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < RANK_SLOTS; k++)
-      if (slot[k] < limit) b.ents[slot[k]] = key;
-  } else if (n > 0 && n <= kBig) {
-    // more than RANK_SLOTS binned tiles: returning atomics on the shared sub-bin, eight in flight at a time
+  if (n > 0 && n <= kBig) {
+    // eight binned tiles at a time: the returning atomics are independent and overlap their L2 round trips (a typical
+    // splat keeps 2-4 of its tiles, so most threads need a single round)
+    const unsigned long long key = ((unsigned long long)depth_bits << 32) | (unsigned)idx;
+    unsigned* cur = im.tile_cursor + subbin_of(idx) * T;
     constexpr int kFlight = 8;
     while (mask) {
       unsigned slot[kFlight];
@@ -179,7 +157,7 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
         if (mask) {
           const int i = __ffs(mask) - 1;
           mask &= mask - 1;
-          slot[k] = atomicAdd(shared_cur + (y0 + i / w) * gx + x0 + i % w, 1u);
+          slot[k] = atomicAdd(cur + (y0 + i / w) * gx + x0 + i % w, 1u);
         }
       }
 #pragma unroll

@@ -45,7 +45,6 @@ struct GeomView {      // carved from the geometry buffer, all 256-B aligned
   int* radii;          // [P] (internal copy; the caller's radii array is also written)
   uint32_t* tiles_touched;  // [P] area of the tile rect (the reference's tiles_touched)
   uint32_t* tile_mask;      // [P] rects of <= 32 tiles: bit i set <=> tile i (row-major in the rect) is binned
-  uint32_t* tile_rank;      // [P][RANK_SLOTS] ranked Gaussians: rank of the k-th binned tile's instance in its (tile, sub-bin)
   float* grad;         // [P][GRAD_F] backward scratch
 };
 struct ImageView {
@@ -144,17 +143,7 @@ __device__ __forceinline__ float4 act_normalize(float4 q, float* inv_norm = null
   if (inv_norm) *inv_norm = 1.0f / n;
   return make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
 }
-// Sub-bin of a Gaussian's tile instances.  "Ranked" Gaussians -- a rect of at most 32 tiles of which at most
-// RANK_SLOTS are binned -- use sub-bins 0..SUBBINS-2 (by index) and keep the rank every counting atomic returned, so
-// the scatter pass places their entries with plain stores; everything else shares the last sub-bin and takes its
-// slots with atomics at scatter time.  The two numbering domains never mix inside a (tile, sub-bin) segment.
-constexpr int RANK_SLOTS = 8;
-__device__ __forceinline__ bool is_ranked(int rect_tiles, uint32_t mask) {
-  return rect_tiles > 0 && rect_tiles <= 32 && __popc(mask) <= RANK_SLOTS;
-}
-__device__ __forceinline__ int subbin_of(int gaussian_idx, bool ranked) {
-  return ranked ? gaussian_idx % (SUBBINS - 1) : SUBBINS - 1;
-}
+__device__ __forceinline__ int subbin_of(int gaussian_idx) { return gaussian_idx & (SUBBINS - 1); }
 __device__ __forceinline__ uint2 pack_rect(int xmin, int ymin, int xmax, int ymax) {
   return make_uint2((unsigned)xmin | ((unsigned)xmax << 16), (unsigned)ymin | ((unsigned)ymax << 16));
 }

@@ -405,31 +405,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) k_preprocess_fwd(FwdArgs a, Ge
   }
   // per-tile instance histogram (level 1 of the two-level binning; replaces InclusiveSum +
   // duplicateWithKeys offsets, rasterizer_impl.cu:280-300)
-  const int T = a.gx * a.gy;
-  const int rw = x1 - x0;
-  if (is_ranked((int)tiles, tmask)) {
-    // returning atomics, all in flight together: the rank of each instance inside its (tile, sub-bin) segment is kept
-    // for the scatter pass (no second atomic pass for these Gaussians)
-    uint32_t* cnt = im.tile_count + subbin_of(idx, true) * T;
-    uint32_t rk[RANK_SLOTS];
-    uint32_t m = tmask;
-#pragma unroll
-    for (int k = 0; k < RANK_SLOTS; k++) {
-      rk[k] = 0;
-      if (m) {
-        const int i = __ffs(m) - 1;
-        m &= m - 1;
-        rk[k] = atomicAdd(cnt + (y0 + i / rw) * a.gx + x0 + i % rw, 1u);
-      }
-    }
-    uint4* dst = reinterpret_cast<uint4*>(g.tile_rank + (size_t)idx * RANK_SLOTS);
-    dst[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
-    if (__popc(tmask) > 4) dst[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
-    tmask = 0;  // done: nothing left for the shared sub-bin below
-  }
-  // everything else (more than RANK_SLOTS binned tiles, or a rect of more than 32 tiles): the shared sub-bin
-  for_each_tile(x0, y0, x1, y1, tmask, a.gx, [&](int tile, unsigned) {
-    atomicAdd(&im.tile_count[subbin_of(0, false) * T + tile], 1u);
+  const int T = a.gx * a.gy, warp_base = idx - (int)(threadIdx.x & 31);
+  for_each_tile(x0, y0, x1, y1, tmask, a.gx, [&](int tile, unsigned src) {
+    atomicAdd(&im.tile_count[subbin_of(warp_base + (int)src) * T + tile], 1u);
   });
   if ((bulk || rows) && threadIdx.x == 0) bar_wait0(&sh_bar);  // the copies must have landed before the CTA retires
 }

@@ -31,7 +31,7 @@ def test_host_only_entry_points():
     assert L.gsr_abi_version() == 1
     g1, g2 = L.gsr_geometry_bytes(1000), L.gsr_geometry_bytes(2000)
     assert 0 < g1 < g2 and g2 < 2 * g1 + 8192
-    assert L.gsr_geometry_bytes(1_000_000) < 176 * 1_000_000  # ~173 B per Gaussian of forward+backward state
+    assert L.gsr_geometry_bytes(1_000_000) < 144 * 1_000_000  # ~141 B per Gaussian of forward+backward state
     i1 = L.gsr_image_bytes(1920, 1080)
     assert 8 * 1920 * 1080 <= i1 < 9 * 1920 * 1080 + 1_000_000
     assert L.gsr_binning_bytes(0) >= 0 and 20 * 2**20 <= L.gsr_binning_bytes(10**6) < 21 * 2**20  # 20 B per instance, 1 Mi granules
