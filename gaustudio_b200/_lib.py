@@ -34,6 +34,7 @@ SIGNATURES = {
     "gsr_extract_normals": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _P, _F, _F, _P, _P, _P, _P]),
     "gsr_normal_fusion_pass": (_I, [_L, _P, _P, _P, _I, _P, _F, _F, _F, _P, _F, _P, _P, _P, _P]),
     "gsr_normal_fusion_mean": (_I, [_I, _P, _P, _P, _P]),
+    "gsr_knn_grid": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "gsr_adam_step": (_I, [_I, _P, C.c_double, C.c_double, C.c_double, _L, _I, _F, _I, _P]),
     "gsr_profile_enable": (_I, [_I]),
     "gsr_profile_read": (_I, [_P, _P]),

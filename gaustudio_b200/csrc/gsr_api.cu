@@ -554,6 +554,17 @@ int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_wei
   return check(cudaGetLastError(), "normal_fusion_mean") ? 0 : -1;
 }
 
+int gsr_knn_grid(int n, int k, const float* points, const int* cell_start, const float* grid, int* out_index,
+                 float* out_dist, void* stream) {
+  if (n <= 0) return 0;
+  if (!points || !cell_start || !grid || !out_index || !out_dist) { g_err = "gsr_knn_grid: null pointer"; return -1; }
+  if (launch_knn_grid(n, k, points, cell_start, grid, out_index, out_dist, (cudaStream_t)stream) < 0) {
+    g_err = "gsr_knn_grid: k must be 1, 4, 8, 10 or 16";
+    return -1;
+  }
+  return check(cudaGetLastError(), "knn_grid") ? 0 : -1;
+}
+
 int gsr_adam_step(int n_groups, const gsr_adam_group* groups, double beta1, double beta2, double eps, int64_t step,
                   int decoupled, float grad_scale, int zero_grad, void* stream) {
   if (n_groups <= 0) return 0;

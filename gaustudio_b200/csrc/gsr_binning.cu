@@ -19,6 +19,7 @@
 // (tile, depth bits, gaussian index).  Level 2 compares whole 64-bit entries, so the result never depends on
 // the (non-deterministic) arrival order of the level-1 scatter.
 #include "gsr_internal.cuh"
+#include <cstdlib>
 
 
 namespace gsr {
@@ -36,7 +37,7 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_TPT = 8;
 constexpr int SCAN_TILES = SCAN_THREADS * SCAN_TPT;
 constexpr int SORT_CAP_SMALL_ = 6144;  // == SORT_CAP_SMALL below
-__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T, int longest_first) {
   __shared__ unsigned total[SCAN_TILES];  // tile totals, then their exclusive prefix within the round
   __shared__ unsigned warp_sums[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,6 +105,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T)
   // Longest-first launch order for the one-CTA-per-tile kernels (sort, compositing): a counting sort of the tiles into
   // 64 size classes, heaviest class first.  Within a class the order is whatever the atomics give -- it only decides
   // which CTA index works on which tile, never a result.
+  if (!longest_first) {  // raster order
+    for (int t = tid; t < T; t += SCAN_THREADS) im.tile_order[t] = (uint32_t)t;
+    return;
+  }
   __shared__ unsigned cls_count[64], cls_start[64];
   if (tid < 64) cls_count[tid] = 0;
   __syncthreads();  // also makes this CTA's tile_range writes visible to itself
@@ -367,7 +372,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
 
 }  // namespace
 
-void launch_tile_scan(ImageView im, int T, cudaStream_t st) { k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(im, T); }
+// GSR_TILE_ORDER=0 (read once per process): one-CTA-per-tile kernels take their tiles in raster order instead of
+// longest-first (the A/B of DESIGN.md 3.4)
+static bool longest_first() {
+  static const bool on = [] { const char* e = getenv("GSR_TILE_ORDER"); return !(e && e[0] == '0'); }();
+  return on;
+}
+void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
+  k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(im, T, longest_first() ? 1 : 0);
+}
 
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
   k_scatter<<<(P + 255) / 256, 256, 0, st>>>(P, gx, T, g, im, b);

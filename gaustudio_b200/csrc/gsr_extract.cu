@@ -190,6 +190,86 @@ void launch_fusion_mean(int P, const float* sum_normals, const float* sum_weight
 
 }  // namespace gsr
 
+// ---- k nearest neighbours on a uniform grid (neighbour search of extract_pcd.py:170-181, there scipy cKDTree on the host)
+// One thread per query point (points are sorted by cell, so a warp's queries are neighbours in space and walk the same
+// cells).  Rings of cells are scanned outwards; after the cube of radius r cells every point outside it is farther
+// than r * cell_size, so the search stops once the k-th best distance is within that bound.
+namespace gsr {
+constexpr int KNN_MAX_K = 16;
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_grid(int n, const float* __restrict__ pts, const int* __restrict__ cell_start,
+                                                  const float* __restrict__ grid, int* __restrict__ out_index,
+                                                  float* __restrict__ out_dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ox = grid[0], oy = grid[1], oz = grid[2], inv_h = grid[3];
+  const int dx = (int)grid[4], dy = (int)grid[5], dz = (int)grid[6];
+  const float h = 1.0f / inv_h;
+  const float qx = pts[3 * i], qy = pts[3 * i + 1], qz = pts[3 * i + 2];
+  const int cx = min(dx - 1, max(0, (int)floorf((qx - ox) * inv_h)));
+  const int cy = min(dy - 1, max(0, (int)floorf((qy - oy) * inv_h)));
+  const int cz = min(dz - 1, max(0, (int)floorf((qz - oz) * inv_h)));
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { bd[k] = 3.0e38f; bi[k] = -1; }
+  const int rmax = max(dx, max(dy, dz));
+  for (int r = 0; r <= rmax; r++) {
+    // the shell of cells at Chebyshev distance exactly r from the query's cell
+    auto scan = [&](int x, int y, int z) {
+      const int c = (z * dy + y) * dx + x;
+      for (int j = cell_start[c]; j < cell_start[c + 1]; j++) {
+        const float ex = pts[3 * j] - qx, ey = pts[3 * j + 1] - qy, ez = pts[3 * j + 2] - qz;
+        float d = ex * ex + ey * ey + ez * ez;
+        if (d < bd[K - 1] || (d == bd[K - 1] && j < bi[K - 1])) {
+          int id = j;
+#pragma unroll
+          for (int k = 0; k < K; k++) {  // insertion into the ascending list (ties: lower index first)
+            const bool before = d < bd[k] || (d == bd[k] && id < bi[k]);
+            const float td = before ? bd[k] : d;
+            const int ti = before ? bi[k] : id;
+            bd[k] = before ? d : bd[k];
+            bi[k] = before ? id : bi[k];
+            d = td; id = ti;
+          }
+        }
+      }
+    };
+    for (int z = max(0, cz - r); z <= min(dz - 1, cz + r); z++)
+      for (int y = max(0, cy - r); y <= min(dy - 1, cy + r); y++) {
+        const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+        if (face || r == 0) {
+          for (int x = max(0, cx - r); x <= min(dx - 1, cx + r); x++) scan(x, y, z);
+        } else {  // interior row of the shell: only its two end cells
+          if (cx - r >= 0) scan(cx - r, y, z);
+          if (cx + r <= dx - 1) scan(cx + r, y, z);
+        }
+      }
+    const float bound = (float)r * h;  // everything not scanned yet is farther than this
+    if (bi[K - 1] >= 0 && bd[K - 1] <= bound * bound) break;
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    out_index[(size_t)i * K + k] = bi[k];
+    out_dist[(size_t)i * K + k] = bi[k] >= 0 ? sqrtf(bd[k]) : __int_as_float(0x7f800000);
+  }
+}
+
+int launch_knn_grid(int n, int k, const float* pts, const int* cell_start, const float* grid, int* out_index,
+                    float* out_dist, cudaStream_t st) {
+  const int blocks = (n + 127) / 128;
+  switch (k) {
+    case 1: k_knn_grid<1><<<blocks, 128, 0, st>>>(n, pts, cell_start, grid, out_index, out_dist); break;
+    case 4: k_knn_grid<4><<<blocks, 128, 0, st>>>(n, pts, cell_start, grid, out_index, out_dist); break;
+    case 8: k_knn_grid<8><<<blocks, 128, 0, st>>>(n, pts, cell_start, grid, out_index, out_dist); break;
+    case 10: k_knn_grid<10><<<blocks, 128, 0, st>>>(n, pts, cell_start, grid, out_index, out_dist); break;
+    case 16: k_knn_grid<16><<<blocks, 128, 0, st>>>(n, pts, cell_start, grid, out_index, out_dist); break;
+    default: return -1;
+  }
+  return 0;
+}
+}  // namespace gsr
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fused multi-tensor Adam / AdamW: the reference steps torch.optim.AdamW over five parameter
 // groups (gaustudio/pipelines/optimizers/base.py:19-20, configs/vanilla.yaml:30-46).  One launch updates every

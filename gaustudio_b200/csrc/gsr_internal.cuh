@@ -241,6 +241,8 @@ void launch_fusion_pass(long long n, const long long* ids, const float* normals,
                         const float* xyz, float tx, float ty, float tz, const float* mean, float thresh,
                         float* sum_normals, float* sum_weights, unsigned char* touched, cudaStream_t st);
 void launch_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean, cudaStream_t st);
+int launch_knn_grid(int n, int k, const float* pts, const int* cell_start, const float* grid, int* out_index,
+                    float* out_dist, cudaStream_t st);  // -1: unsupported k (1, 4, 8, 10, 16)
 }  // namespace gsr
 struct gsr_adam_group;
 namespace gsr {

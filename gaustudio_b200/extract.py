@@ -9,8 +9,8 @@
 
 The reference moves every depth map to the host for OpenCV (dilate + bilateralFilter) and back; here the filter,
 the normal extraction and the fusion passes are CUDA kernels behind the C ABI (include/gsr.h) and nothing is
-synchronised per view.  Only the k-nearest-neighbour search of the final smoothing stays on the host (scipy's
-cKDTree, exactly as in the reference); its weighting runs on the device.
+synchronised per view.  The k-nearest-neighbour search of the final smoothing (scipy's cKDTree on the host in the
+reference) is a uniform-grid search on the device as well (`knn`, gsr_knn_grid).
 """
 import ctypes as C
 
@@ -173,14 +173,54 @@ def normal_fusion(pcd, all_ids_list, all_normals_list, all_confidences_list, cam
     mean = mean[unique_ids]
     if not smooth or unique_ids.numel() == 0:
         return unique_ids, mean
-    # spatial smoothing over the 10 nearest surface points (extract_pcd.py:170-181); neighbour search on the host
-    from scipy.spatial import cKDTree
-    pts = xyz[unique_ids].cpu().numpy()
-    dist, idx = cKDTree(pts).query(pts, k=min(10, len(pts)))  # (the reference needs >= 10 surface points)
-    dist, idx = dist.reshape(len(pts), -1), idx.reshape(len(pts), -1)
-    w = torch.exp(-torch.from_numpy(dist).to(dev) / 0.1)
-    sm = (mean[torch.from_numpy(idx).to(dev)].double() * w.unsqueeze(-1)).sum(1).float()
+    # spatial smoothing over the 10 nearest surface points (extract_pcd.py:170-181: scipy cKDTree on the host there);
+    # here the neighbour search stays on the device (the reference needs >= 10 surface points)
+    dist, idx = knn(xyz[unique_ids], k=min(10, int(unique_ids.numel())))
+    w = torch.exp(-dist.double() / 0.1)
+    sm = (mean[idx].double() * w.unsqueeze(-1)).sum(1).float()
     return unique_ids, torch.nn.functional.normalize(sm, p=2, dim=1)
+
+
+_KNN_K = (1, 4, 8, 10, 16)
+
+
+def knn(points, k=10):
+    """k nearest neighbours of every point among `points` [n,3] (float32, CUDA) -> (dist [n,k] float32, idx [n,k] int64),
+    ascending distance with the point itself first -- what `cKDTree(points).query(points, k)` returns
+    (extract_pcd.py:170-171), without leaving the device.  Uniform-grid search (gsr_knn_grid): the points are sorted by
+    cell with torch ops, the bounding box / cell size never come back to the host."""
+    _need_cuda(points, "points")
+    pts = points.detach().float().contiguous()
+    n, dev = pts.shape[0], pts.device
+    if k not in _KNN_K or n <= k:  # tiny inputs / unusual k: exact all-pairs search (still on the device)
+        d = torch.cdist(pts.double(), pts.double())
+        dist, idx = d.topk(min(k, n), dim=1, largest=False)
+        return dist.float(), idx
+    G = min(256, max(8, 1 << math.ceil(math.log2(max(n, 2) ** (1.0 / 3.0)))))
+    lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
+    ext = (hi - lo).clamp_min(1e-12)
+    inv_h = 1.0 / (ext.max() / G * 1.0001 + 1e-12)
+    dims = torch.clamp(torch.ceil(ext * inv_h), min=1.0, max=float(G))
+    cell = torch.minimum(torch.clamp(((pts - lo) * inv_h).floor(), min=0.0), dims - 1.0)
+    cid = ((cell[:, 2] * dims[1] + cell[:, 1]) * dims[0] + cell[:, 0]).long()
+    order = torch.argsort(cid, stable=True)
+    sorted_pts = pts[order].contiguous()
+    counts = torch.zeros(G ** 3 + 1, dtype=torch.int64, device=dev)
+    counts.scatter_add_(0, cid + 1, torch.ones_like(cid))
+    cell_start = torch.cumsum(counts, 0).to(torch.int32).contiguous()
+    grid = torch.cat([lo, inv_h.reshape(1), dims, torch.zeros(1, device=dev)]).float().contiguous()
+    out_i = torch.empty(n, k, dtype=torch.int32, device=dev)
+    out_d = torch.empty(n, k, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().gsr_knn_grid(n, k, _ptr(sorted_pts), _ptr(cell_start), _ptr(grid), _ptr(out_i), _ptr(out_d),
+                                     _stream(dev))
+    if rc < 0:
+        raise RuntimeError("gsr_knn_grid failed: " + _lib.last_error())
+    dist = torch.empty_like(out_d)
+    idx = torch.empty(n, k, dtype=torch.int64, device=dev)
+    dist[order] = out_d                     # rows back to the caller's order ...
+    idx[order] = order[out_i.long()]        # ... and neighbour indices back to the caller's numbering
+    return dist, idx
 
 
 def SH2RGB(sh):

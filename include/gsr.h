@@ -160,6 +160,17 @@ int gsr_normal_fusion_pass(int64_t n, const int64_t* ids, const float* normals, 
 int gsr_normal_fusion_mean(int P, const float* sum_normals, const float* sum_weights, float* mean_normals,
                            void* stream);
 
+/* k nearest neighbours among n points (the neighbour search of the fusion's final smoothing, extract_pcd.py:170-181,
+ * done there on the host with scipy's cKDTree: a D2H + H2D round trip per extraction).  Uniform-grid search on the device.
+ *   points      float[n*3], SORTED by cell id of the grid below (cell = (z*dims.y + y)*dims.x + x)
+ *   cell_start  int32[num_cells + 1]: index of the first point of every cell (exclusive prefix of the cell counts)
+ *   grid        DEVICE float[8]: origin.xyz, 1/cell_size, dims.xyz (as floats), unused -- kept on the device so the
+ *               caller never has to read the bounding box back
+ *   out_index   int32[n*k]: neighbours of point i (indices into `points`), ascending distance, the point itself first;
+ *   out_dist    float[n*k]: their Euclidean distances.  k <= 16.  Entries are -1 / +inf if fewer than k points exist. */
+int gsr_knn_grid(int n, int k, const float* points, const int* cell_start, const float* grid, int* out_index,
+                 float* out_dist, void* stream);
+
 /* ---- optimizer step after the path ----
  * Fused multi-tensor Adam / AdamW: replaces `torch.optim.<optimizer_name>(param_groups, **args).step()` of
  * gaustudio/pipelines/optimizers/base.py:19-30 (+ zero_grad, :32-34) for optimizer_name in {Adam, AdamW}

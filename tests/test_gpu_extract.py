@@ -164,3 +164,26 @@ def test_dense_views_fuse_like_compact_views_and_negative_ids_are_skipped():
     uc, nc = extract.normal_fusion(model, [ids0] + lists[True][0][1:], [n0] + lists[True][1][1:], [c0] + lists[True][2][1:],
                                    cams, smooth=False)
     assert torch.equal(ua, uc) and torch.allclose(torch.nan_to_num(na), torch.nan_to_num(nc), atol=1e-6)
+
+
+@pytest.mark.parametrize("n,shape", [(5000, "ball"), (40000, "shell"), (300, "line")])
+def test_device_knn_matches_ckdtree(n, shape):
+    """The neighbour search of the fusion's smoothing (extract_pcd.py:170-171, scipy cKDTree there) on the device."""
+    from scipy.spatial import cKDTree
+    from gaustudio_b200.extract import knn
+    g = torch.Generator().manual_seed(n)
+    p = torch.randn(n, 3, generator=g)
+    if shape == "shell":      # a surface: what the extraction produces
+        p = p / p.norm(dim=1, keepdim=True) * (1 + 0.01 * torch.randn(n, 1, generator=g))
+    elif shape == "line":     # degenerate extents: one cell row
+        p = torch.stack([torch.linspace(0, 1, n), torch.zeros(n), torch.zeros(n)], 1) + 1e-4 * p
+    p = p.float()
+    dist, idx = knn(p.to(DEV), k=10)
+    rd, ri = cKDTree(p.numpy()).query(p.numpy(), k=10)
+    assert torch.equal(idx[:, 0].cpu(), torch.arange(n)) and float(dist[:, 0].abs().max()) == 0.0
+    np.testing.assert_allclose(dist.cpu().numpy(), rd, rtol=1e-5, atol=1e-6)
+    same = (idx.cpu().numpy() == ri)
+    assert same.mean() > 0.999  # equal-distance neighbours may swap places
+    # unusual k / tiny inputs take the exact all-pairs path
+    d3, i3 = knn(p[:7].to(DEV), k=10)
+    assert d3.shape == (7, 7) and torch.equal(i3[:, 0].cpu(), torch.arange(7))
