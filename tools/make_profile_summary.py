@@ -38,7 +38,8 @@ for r in rows[2:]:
     def mb(k):
         v = float(r[idx[k]].replace(",", "")); u = units[idx[k]]
         return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(u, 1)
-    traffic[name] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+    base = name.split("<")[0]  # template instantiations of one kernel count together
+    traffic[base] = traffic.get(base, 0.0) + mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
 open(os.path.join(out, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
 grp = {"preprocess_fwd": traffic.get("k_preprocess_fwd"), "render_fwd": traffic.get("k_render_fwd"), "render_bwd": traffic.get("k_render_bwd"),
        "preprocess_bwd": traffic.get("k_preprocess_bwd"),
@@ -49,6 +50,7 @@ tf = os.path.join(out, "ncu_traffic.json")
 if all(grp.values()):
     old = json.load(open(tf)) if os.path.exists(tf) else {}
     old.update(grp)
+    old["_note"] = f"bytes = dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, cfg3 view), from {os.path.basename(rep)}"
     json.dump(old, open(tf, "w"), indent=1)
 if launches:
     rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
