@@ -23,7 +23,7 @@
 //    gradient contributions over its own pixels in registers before the warp-level reduction, so the
 //    transposed shuffle butterfly + predicated red.global run once per (warp region, Gaussian) instead of
 //    once per (8x4 block, Gaussian) -- and instead of 11-12 atomicAdd per (pixel, Gaussian) pair
-//    (backward.cu:559-607).  The per-pair arithmetic is re-derived for instruction count (see bwd_pair):
+//    (backward.cu:559-607).  The per-pair arithmetic is re-derived for instruction count (see the kernel body):
 //    one scalar "behind" recurrence for all five blended channels, and the mean / conic gradients are
 //    accumulated as raw moments of u = dL/dG * G (sum u dx, u dy, u dx^2, u dx dy, u dy^2) that the
 //    per-Gaussian kernel turns into dL/dmean2D and dL/dconic.  Traversal starts at the tile's largest
