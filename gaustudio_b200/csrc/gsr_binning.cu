@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T,
   // Longest-first launch order for the one-CTA-per-tile kernels (sort, compositing): a counting sort of the tiles into
   // 64 size classes, heaviest class first.  Within a class the order is whatever the atomics give -- it only decides
   // which CTA index works on which tile, never a result.
-  if (!longest_first) {  // raster order
+  if (longest_first == 0) {  // raster order
     for (int t = tid; t < T; t += SCAN_THREADS) im.tile_order[t] = (uint32_t)t;
     return;
   }
@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T,
     for (int c = 0; c < 64; c++) { cls_start[c] = run; run += cls_count[c]; }
   }
   __syncthreads();
-  for (int t = tid; t < T; t += SCAN_THREADS) im.tile_order[atomicAdd(&cls_start[size_class(t)], 1u)] = (uint32_t)t;
+  for (int t = tid; t < T; t += SCAN_THREADS) {
+    const unsigned pos = atomicAdd(&cls_start[size_class(t)], 1u);
+    im.tile_order[longest_first == 2 ? (unsigned)T - 1u - pos : pos] = (uint32_t)t;  // 2: shortest first
+  }
 }
 
 // ---- level 1b: scatter one entry per (Gaussian, touched tile) ------------------------------------
@@ -374,12 +377,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
 
 // GSR_TILE_ORDER=0 (read once per process): one-CTA-per-tile kernels take their tiles in raster order instead of
 // longest-first (the A/B of DESIGN.md 3.4)
-static bool longest_first() {
-  static const bool on = [] { const char* e = getenv("GSR_TILE_ORDER"); return !(e && e[0] == '0'); }();
-  return on;
+static int tile_order_mode() {  // 0 raster, 1 longest first (default), 2 shortest first
+  static const int m = [] { const char* e = getenv("GSR_TILE_ORDER"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+  return m;
 }
 void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
-  k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(im, T, longest_first() ? 1 : 0);
+  k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(im, T, tile_order_mode());
 }
 
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {

@@ -2,11 +2,11 @@
 # A/B of the CTA -> tile order of the one-CTA-per-tile kernels: GSR_TILE_ORDER=1 (longest first) vs 0 (raster), bench.py
 # default mode (3 streams + CUDA graphs) and 4 streams, alternating runs.  -> gpurun_out/r2_order*.json
 for i in 1 2; do
-  for o in 1 0; do
+  for o in ${ORDERS:-1 0}; do
     GSR_TILE_ORDER=$o timeout -k 10 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --dropin 0 > gpurun_out/r2_order${o}_$i.json 2>/dev/null
   done
 done
-for o in 1 0; do
+for o in ${ORDERS:-1 0}; do
   GSR_TILE_ORDER=$o timeout -k 10 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --dropin 0 --streams 4 > gpurun_out/r2_order${o}_s4.json 2>/dev/null
   GSR_TILE_ORDER=$o timeout -k 10 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --dropin 1 --streams 1 --graph 0 > gpurun_out/r2_order${o}_s1.json 2>/dev/null
 done
