@@ -52,6 +52,12 @@ def restore_pipeline(state):
         setattr(_pipeline, k, state[k])
 
 
+def set_tile_order(mode):
+    """CTA -> tile order of the per-tile kernels (gsr_set_tile_order): 1 longest first (default), 0 raster, 2 shortest
+    first, < 0 back to the default.  Process-wide; returns the previous mode.  Results never depend on it."""
+    return int(_lib.lib().gsr_set_tile_order(int(mode)))
+
+
 def last_num_binned():
     """Tile instances the most recent EXACT-mode forward on this thread actually binned.  The returned `num_rendered`
     keeps the reference's meaning (sum of the tile-rect areas); (Gaussian, tile) pairs that cannot reach alpha >= 1/255

@@ -590,6 +590,8 @@ int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_b
   return check(cudaGetLastError(), "debug_export") ? 0 : -1;
 }
 
+int gsr_set_tile_order(int mode) { return set_tile_order(mode); }
+
 int gsr_profile_enable(int on) {
   g_prof_on = on != 0;
   return 0;

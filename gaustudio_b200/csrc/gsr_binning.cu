@@ -19,6 +19,7 @@
 // (tile, depth bits, gaussian index).  Level 2 compares whole 64-bit entries, so the result never depends on
 // the (non-deterministic) arrival order of the level-1 scatter.
 #include "gsr_internal.cuh"
+#include <atomic>
 #include <cstdlib>
 
 
@@ -377,9 +378,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
 
 // GSR_TILE_ORDER=0 (read once per process): one-CTA-per-tile kernels take their tiles in raster order instead of
 // longest-first (the A/B of DESIGN.md 3.4)
+static std::atomic<int> g_tile_order{-1};  // gsr_set_tile_order; < 0: the default below
+int set_tile_order(int mode) { return g_tile_order.exchange(mode > 2 ? -1 : mode); }
 static int tile_order_mode() {  // 0 raster, 1 longest first (default), 2 shortest first
-  static const int m = [] { const char* e = getenv("GSR_TILE_ORDER"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
-  return m;
+  static const int dflt = [] { const char* e = getenv("GSR_TILE_ORDER"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+  const int m = g_tile_order.load();
+  return m >= 0 ? m : dflt;
 }
 void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
   k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(im, T, tile_order_mode());

@@ -99,6 +99,7 @@ struct FwdArgs {
 // ---- launch wrappers (each enqueues on `st`) ----
 void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStream_t st);
 void launch_tile_scan(ImageView im, int T, cudaStream_t st);
+int set_tile_order(int mode);  // gsr_set_tile_order
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st);
 // splat_tensor_map: a CUtensorMap over the [P][12 float] splat array (TMA gather4 staging) or nullptr (LDGSTS staging)

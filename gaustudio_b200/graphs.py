@@ -45,6 +45,9 @@ class GraphedViewStep:
     captures the in-place accumulation into them, so several replays sum their gradients into the same buffers -- the
     caller zeroes them (the fused optimizer step does, `zero_grad=True`).  They are zeroed once after the capture.
 
+    `tile_order` (baked into the captured launches): graphs exist to keep several views in flight on different streams,
+    where raster order (0) packs better than the library's longest-first default (`_C.set_tile_order`); restored after.
+
     The fixed-capacity forward mode is only active during warm-up and capture: the caller's own forward mode
     (`_C.set_pipelined`) is restored before the constructor returns, so eager renders afterwards behave as before.
 
@@ -53,11 +56,12 @@ class GraphedViewStep:
     (cudaErrorStreamCaptureImplicit).  Eager steps after the capture are fine."""
 
     def __init__(self, renderer, model, loss_fn, example_cameras, capacity=None, post_fn=None, device=None,
-                 accumulate=False):
+                 accumulate=False, tile_order=0):
         dev = device or model._xyz.device
         self.dev, self.model = dev, model
         cams = list(example_cameras)
         saved = _C.pipeline_state()
+        saved_order = _C.set_tile_order(tile_order)
         try:
             if capacity is None:  # largest instance count over the example views (eager, exact mode) + 30 %
                 _C.set_pipelined(False)
@@ -108,6 +112,7 @@ class GraphedViewStep:
             self.rmax.zero_()
         finally:
             _C.restore_pipeline(saved)
+            _C.set_tile_order(saved_order)
 
     @staticmethod
     def _count(renderer, cam, model, dev):

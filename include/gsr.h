@@ -209,6 +209,13 @@ int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_b
                      float* depths, float* rgb, float* cov3D, uint32_t* tiles_touched, unsigned char* clamped,
                      void* stream);
 
+/* CTA -> tile order of the one-CTA-per-tile kernels (per-tile sort, compositing forward / backward): 1 = longest tile
+ * first (default: shortest makespan when ONE view is in flight: -9 % / -6 % on the two compositing kernels at cfg 3),
+ * 0 = raster order (about 1.5 % more throughput when several views are pipelined on different streams: each kernel's
+ * long tail of crowded tiles overlaps the next kernel), 2 = shortest first.  Process-wide; returns the previous mode;
+ * mode < 0 restores the default (or the GSR_TILE_ORDER environment variable).  Results never depend on it. */
+int gsr_set_tile_order(int mode);
+
 /* Optional per-stage device timing (CUDA events recorded on the caller's stream around each kernel).
  * Stages: 0 preprocess_fwd, 1 tile_scan, 2 scatter, 3 tile_sort, 4 render_fwd, 5 render_bwd,
  *         6 preprocess_bwd, 7 depth2normal.  gsr_profile_read synchronises the recorded events, adds their

@@ -346,3 +346,34 @@ def test_graphed_view_step_matches_eager():
             assert float((model._f_rest.grad - gs_g).abs().max()) <= 1e-4 * float(gs_g.abs().max())
     finally:
         _C.set_pipelined(False)
+
+
+def test_tile_order_never_changes_results():
+    """gsr_set_tile_order only decides which CTA works on which tile (longest first / raster / shortest first)."""
+    from gaustudio_b200 import _C, renderers
+    from gaustudio_b200.synthetic import build_config
+    model, cams, c = build_config("cfg2", P=40000, W=320, H=240, K=2)
+    dev = torch.device("cuda")
+    model.to(dev).requires_grad_(True)
+    cam = cams[0].to(dev)
+    r = renderers.make({"name": "vanilla_renderer"})
+    w = torch.randn(3, 240, 320, generator=torch.Generator().manual_seed(2)).to(dev)
+    res = {}
+    prev = _C.set_tile_order(1)
+    try:
+        for mode in (1, 0, 2):
+            _C.set_tile_order(mode)
+            for p in model.parameters_list():
+                p.grad = None
+            out = r.render(cam, model)
+            ((out["render"] * w).sum() + out["rendered_depth"].sum()).backward()
+            res[mode] = ([out[k].detach().clone() for k in ("render", "rendered_depth", "rendered_median_depth",
+                                                            "rendered_final_opacity", "radii")],
+                         [p.grad.clone() for p in model.parameters_list()])
+    finally:
+        _C.set_tile_order(prev)
+    for mode in (0, 2):
+        for a, b in zip(res[1][0], res[mode][0]):
+            assert torch.equal(a, b), mode
+        for a, b in zip(res[1][1], res[mode][1]):
+            assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12, mode  # float reductions: order only
