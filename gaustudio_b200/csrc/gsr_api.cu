@@ -67,6 +67,16 @@ struct Prof {
 };
 }  // namespace
 
+int high_priority() {
+  static const int prio = [] {
+    const char* e = getenv("GSR_PRIORITY");
+    if (e && e[0] == '0') return 0;
+    int least = 0, greatest = 0;
+    return cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess ? greatest : 0;
+  }();
+  return prio;
+}
+
 const DeviceInfo& device_info() {
   static DeviceInfo info[64];
   static std::mutex mu;
@@ -259,7 +269,7 @@ void launch_depth2normal(const float* depth, int W, int H, float fx, float fy, f
                          float dmax, const float* rot, float* out, cudaStream_t st) {
   dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
   // K^-1 entries computed on the host in float like torch.inverse of the float32 intrinsics
-  k_depth2normal<<<grd, blk, 0, st>>>(depth, W, H, 1.0f / fx, 1.0f / fy, -cx / fx, -cy / fy, dmin, dmax, rot, out);
+  launch_high_priority(k_depth2normal, grd, blk, 0, st, depth, W, H, 1.0f / fx, 1.0f / fy, -cx / fx, -cy / fy, dmin, dmax, rot, out);
 }
 
 void launch_depth2point(const float* depth, int W, int H, float fx, float fy, float cx, float cy, const float* c2w,
@@ -330,7 +340,7 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
 
   const unsigned long long cap0 = r_capacity > 0 ? (unsigned long long)r_capacity : ~0ull;
   if (!check(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * T * SUBBINS, st), "memset tile_count")) return -1;
-  k_init_header<<<1, 1, 0, st>>>(im.hdr, cap0);
+  launch_high_priority(k_init_header, dim3(1), dim3(1), 0, st, im.hdr, (unsigned long long)cap0);
   { Prof pf(0, st); launch_preprocess_fwd(a, g, im, st); }
   if (!stage_ok(dbg, st, "preprocess_fwd")) return -1;
   { Prof pf(1, st); launch_tile_scan(im, T, st); }

@@ -386,11 +386,11 @@ static int tile_order_mode() {  // 0 raster, 1 longest first (default), 2 shorte
   return m >= 0 ? m : dflt;
 }
 void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
-  k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(im, T, tile_order_mode());
+  launch_high_priority(k_tile_scan, dim3(1), dim3(SCAN_THREADS), 0, st, im, T, tile_order_mode());
 }
 
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
-  k_scatter<<<(P + 255) / 256, 256, 0, st>>>(P, gx, T, g, im, b);
+  launch_high_priority(k_scatter, dim3((P + 255) / 256), dim3(256), 0, st, P, gx, T, g, im, b);
 }
 
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
@@ -405,9 +405,9 @@ void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t s
     cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
     di.sort_attr_set = true;
   }
-  small<<<T, SORT_THREADS, smem_small, st>>>(g, im, b);
-  mid<<<2 * di.sm_count, SORT_THREADS, smem_mid, st>>>(g, im, b);  // two CTAs per SM draw the 4k-12k tiles
-  big<<<di.sm_count, SORT_THREADS, smem_big, st>>>(g, im, b);      // one CTA per SM draws the rest
+  launch_high_priority(small, dim3(T), dim3(SORT_THREADS), smem_small, st, g, im, b);
+  launch_high_priority(mid, dim3(2 * di.sm_count), dim3(SORT_THREADS), smem_mid, st, g, im, b);  // two CTAs per SM draw the 6k-12k tiles
+  launch_high_priority(big, dim3(di.sm_count), dim3(SORT_THREADS), smem_big, st, g, im, b);      // one CTA per SM draws the rest
 }
 
 }  // namespace gsr

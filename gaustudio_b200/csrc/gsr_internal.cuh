@@ -65,6 +65,25 @@ struct BinView {               // point_list comes FIRST: its address does not d
   unsigned long long* ents2;  // [cap] scratch of the level-2 sort for tiles that exceed shared memory
 };
 
+// Launch with an execution priority (cudaLaunchAttributePriority; recorded in the kernel node under graph capture).
+// The per-Gaussian and binning kernels are memory- / latency-bound, the compositing kernels issue-bound; when several
+// views are in flight on different streams the block scheduler hands out CTAs kernel by kernel in launch order, so
+// without a hint a short latency-bound kernel of view B waits behind all 8160 CTAs of view A's compositing kernel and
+// the two kinds of work never overlap.  With the high priority its CTAs take the slots that free up first.
+// GSR_PRIORITY=0 (read once) launches everything at the default priority.
+int high_priority();  // the device's greatest stream priority, or 0 (= default) when disabled (gsr_api.cu)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_high_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributePriority;
+  attr[0].val.priority = high_priority();
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Per-device facts and one-time kernel attributes of the CURRENT device (cached; gsr_api.cu).
 struct DeviceInfo {
   int sm_count = 0;

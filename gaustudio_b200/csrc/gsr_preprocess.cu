@@ -719,7 +719,7 @@ void launch_preprocess_fwd(const FwdArgs& a, GeomView g, ImageView im, cudaStrea
     cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     di.pre_fwd_smem = smem;
   }
-  k_preprocess_fwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g, im);
+  launch_high_priority(k_preprocess_fwd, dim3((a.P + PRE_THREADS - 1) / PRE_THREADS), dim3(PRE_THREADS), smem, st, a, g, im);
 }
 void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st) {
   const size_t smem = a.sh_bulk ? (size_t)PRE_THREADS * a.M * 12 : (a.sh_rows ? (size_t)PRE_THREADS * SH_ROW * 4 : 0);
@@ -728,7 +728,7 @@ void launch_preprocess_bwd(const BwdArgs& a, GeomView g, cudaStream_t st) {
     cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     di.pre_bwd_smem = smem;
   }
-  k_preprocess_bwd<<<(a.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, st>>>(a, g);
+  launch_high_priority(k_preprocess_bwd, dim3((a.P + PRE_THREADS - 1) / PRE_THREADS), dim3(PRE_THREADS), smem, st, a, g);
 }
 void launch_mark_visible(int P, const float* means3D, const float* view, const float*, unsigned char* present,
                          cudaStream_t st) {
