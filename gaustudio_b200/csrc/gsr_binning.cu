@@ -131,7 +131,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T,
 }
 
 // ---- level 1b: scatter one entry per (Gaussian, touched tile) ------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b) {
+#ifndef GSR_SCATTER_THREADS
+#define GSR_SCATTER_THREADS 256
+#endif
+constexpr int SCATTER_THREADS = GSR_SCATTER_THREADS;
+__global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   unsigned depth_bits = 0, mask = 0;
@@ -194,6 +198,14 @@ __global__ void __launch_bounds__(256) k_scatter(int P, int gx, int T, GeomView 
 // entry (depth bits << 32 | gaussian index).  Comparing the whole entry yields the reference's order
 // (stable by depth == ties in ascending Gaussian index) with no dependence on the scatter's arrival order.
 constexpr int SORT_THREADS = 512;
+#ifndef GSR_SORT_THREADS_TINY
+#define GSR_SORT_THREADS_TINY 128
+#endif
+#ifndef GSR_SORT_CAP_TINY
+#define GSR_SORT_CAP_TINY 1024
+#endif
+constexpr int SORT_THREADS_TINY = GSR_SORT_THREADS_TINY;  // CTA size of the tier that owns the tiles with <= SORT_CAP_TINY instances
+constexpr int SORT_CAP_TINY = GSR_SORT_CAP_TINY;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 // Three launches cover every tile: a small-footprint kernel (one CTA per tile, 4 CTAs/SM) for tiles up to
 // SORT_CAP_SMALL entries, a two-CTAs-per-SM kernel for tiles up to SORT_CAP_MID and a one-CTA-per-SM kernel with
@@ -245,6 +257,11 @@ __device__ __forceinline__ void warp_sort_mem(u64* k, unsigned m, unsigned lane)
   }
 }
 
+// r += (o < k): one predicated add (the compiler's own form is an add plus a predicated move on the dependent chain)
+__device__ __forceinline__ void count_if_less(unsigned& r, u64 o, u64 k) {
+  asm("{ .reg .pred p; setp.lt.u64 p, %1, %2; @p add.u32 %0, %0, 1; }" : "+r"(r) : "l"(o), "l"(k));
+}
+
 template <int NB> struct SortShared {
   unsigned cnt[NB];        // bucket sizes, then running cursors of the split
   unsigned start[NB + 1];  // exclusive prefix of the bucket sizes
@@ -254,23 +271,26 @@ template <int NB> struct SortShared {
 
 // CAP: entries held in shared memory; this launch owns the tiles with MIN_N < n <= MAX_N entries (MAX_N = 0: no upper
 // bound; beyond CAP the tile is sorted in the global scratch); NB: depth buckets of the MSD split; TIER: ticket index.
-template <int CAP, int MIN_N, int MAX_N, int NB, int TIER>
-__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageView im, BinView b) {
+// DIRECT: one CTA per tile (blockIdx -> tile_order); otherwise CTAs draw tickets into the list of crowded tiles.
+// THREADS: CTA size (<= SORT_THREADS).
+template <int CAP, int MIN_N, int MAX_N, int NB, int TIER, bool DIRECT, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_tile_sort(GeomView g, ImageView im, BinView b) {
+  constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) u64 sort_smem[];
   __shared__ SortShared<NB> sh;
   __shared__ unsigned sh_work;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // small launch: one CTA per tile.  crowded launches: CTAs draw tiles from the compact list of crowded tiles.
-  const unsigned num_work = MIN_N == 0 ? gridDim.x : im.hdr->num_big;
+  const unsigned num_work = DIRECT ? gridDim.x : im.hdr->num_big;
   for (unsigned work = blockIdx.x;; work += gridDim.x) {
-  if (MIN_N != 0) {
+  if (!DIRECT) {
     __syncthreads();  // everybody is done with the previous tile (and with sh_work)
     if (tid == 0) sh_work = atomicAdd(&im.hdr->ticket[TIER], 1u);
     __syncthreads();
     work = sh_work;
   }
   if (work >= num_work) break;
-  const unsigned tile = MIN_N == 0 ? im.tile_order[work] : im.big_tiles[work];
+  const unsigned tile = DIRECT ? im.tile_order[work] : im.big_tiles[work];
   const uint2 range = im.tile_range[tile];
   const unsigned n = range.y - range.x;
   if (n <= (unsigned)MIN_N || (MAX_N != 0 && n > (unsigned)MAX_N)) continue;  // another launch owns this tile
@@ -293,13 +313,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     // tile with more instances than fit).
     const u64* A = seg;
     u64* B = in_smem ? sort_smem : b.ents2 + range.x;
-    for (unsigned i = tid; i < NB; i += SORT_THREADS) sh.cnt[i] = 0;
+    for (unsigned i = tid; i < NB; i += THREADS) sh.cnt[i] = 0;
     if (tid == 0) { sh.dmin = 0xffffffffu; sh.dmax = 0u; }
     __syncthreads();
     // bucket = linear map of the depth bits from the tile's own [min, max] onto [0, NB): monotone in depth, and
     // balanced even when the tile's depths span several binades but crowd into one of them
     unsigned lo = 0xffffffffu, hi = 0u;
-    for (unsigned i = tid; i < n; i += SORT_THREADS) { const unsigned d = (unsigned)(A[i] >> 32); lo = min(lo, d); hi = max(hi, d); }
+    for (unsigned i = tid; i < n; i += THREADS) { const unsigned d = (unsigned)(A[i] >> 32); lo = min(lo, d); hi = max(hi, d); }
     lo = __reduce_min_sync(FULL, lo); hi = __reduce_max_sync(FULL, hi);
     if (lane == 0) { atomicMin(&sh.dmin, lo); atomicMax(&sh.dmax, hi); }
     __syncthreads();
@@ -314,10 +334,10 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
       const unsigned d = (unsigned)(key >> 32) - dmin;
       return direct ? d : __umulhi(d, mult);
     };
-    for (unsigned i = tid; i < n; i += SORT_THREADS) atomicAdd(&sh.cnt[bucket(A[i])], 1u);
+    for (unsigned i = tid; i < n; i += THREADS) atomicAdd(&sh.cnt[bucket(A[i])], 1u);
     __syncthreads();
-    {  // exclusive scan of the NB bucket sizes: NB / SORT_THREADS consecutive buckets per thread
-      constexpr int PER = (NB + SORT_THREADS - 1) / SORT_THREADS;
+    {  // exclusive scan of the NB bucket sizes: NB / THREADS consecutive buckets per thread
+      constexpr int PER = (NB + THREADS - 1) / THREADS;
       unsigned c[PER], local = 0;
 #pragma unroll
       for (int k = 0; k < PER; k++) { const unsigned i = tid * PER + k; c[k] = i < NB ? sh.cnt[i] : 0u; local += c[k]; }
@@ -328,35 +348,45 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
       __syncthreads();
       unsigned run = v - local;
 #pragma unroll
-      for (int w = 0; w < SORT_WARPS; w++) run += (w < (int)warp) ? sh.wsum[w] : 0u;
+      for (int w = 0; w < WARPS; w++) run += (w < (int)warp) ? sh.wsum[w] : 0u;
 #pragma unroll
       for (int k = 0; k < PER; k++) {
         const unsigned i = tid * PER + k;
         if (i < NB) { sh.start[i] = run; sh.cnt[i] = run; }
         run += c[k];
       }
-      if (tid == SORT_THREADS - 1) sh.start[NB] = run;
+      if (tid == THREADS - 1) sh.start[NB] = run;
     }
     __syncthreads();
-    for (unsigned i = tid; i < n; i += SORT_THREADS) {
+    for (unsigned i = tid; i < n; i += THREADS) {
       const u64 key = A[i];
       B[atomicAdd(&sh.cnt[bucket(key)], 1u)] = key;
     }
     __syncthreads();
-    for (unsigned bk = warp; bk < nb; bk += SORT_WARPS) {
+    for (unsigned bk = warp; bk < nb; bk += WARPS) {
       const unsigned s0 = sh.start[bk], m = sh.start[bk + 1] - s0;
       if (m <= 1) continue;
-      if (m <= 64) {
-        // rank sort, up to two entries per lane: entries are distinct 64-bit values, so an entry's position is
-        // the number of smaller ones (m broadcast reads + compares: cheaper than a bitonic network for the
-        // ~24-entry buckets the split aims at)
+      if (m <= 32) {
+        // rank sort, one entry per lane: entries are distinct 64-bit values, so an entry's position is the number
+        // of smaller ones (m broadcast reads + compares: cheaper than a bitonic network for the ~24-entry buckets
+        // the split aims at)
         const u64 k0 = lane < m ? B[s0 + lane] : ~0ull;
+        unsigned r0 = 0;
+#pragma unroll 8
+        for (unsigned j = 0; j < m; j++) count_if_less(r0, B[s0 + j], k0);
+        __syncwarp();
+        if (lane < m) B[s0 + r0] = k0;
+        __syncwarp();
+      } else if (m <= 64) {
+        // the same with two entries per lane
+        const u64 k0 = B[s0 + lane];
         const u64 k1 = lane + 32 < m ? B[s0 + 32 + lane] : ~0ull;
         unsigned r0 = 0, r1 = 0;
+#pragma unroll 4
         for (unsigned j = 0; j < m; j++) {
           const u64 o = B[s0 + j];
-          r0 += (o < k0) ? 1u : 0u;
-          r1 += (o < k1) ? 1u : 0u;
+          count_if_less(r0, o, k0);
+          count_if_less(r1, o, k1);
         }
         __syncwarp();
         if (lane < m) B[s0 + r0] = k0;
@@ -370,7 +400,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(GeomView g, ImageVie
     sorted = B;
   }
   // the sorted order, as Gaussian indices (what the render kernels walk)
-  for (unsigned i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)sorted[i];
+  for (unsigned i = tid; i < n; i += THREADS) out[i] = (uint32_t)sorted[i];
   }
 }
 
@@ -390,14 +420,18 @@ void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
 }
 
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
-  launch_high_priority(k_scatter, dim3((P + 255) / 256), dim3(256), 0, st, P, gx, T, g, im, b);
+  launch_high_priority(k_scatter, dim3((P + SCATTER_THREADS - 1) / SCATTER_THREADS), dim3(SCATTER_THREADS), 0, st, P, gx, T, g, im, b);
 }
 
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
-  auto small = k_tile_sort<SORT_CAP_SMALL, 0, SORT_CAP_SMALL, 512, 0>;
-  auto mid = k_tile_sort<SORT_CAP_MID, SORT_CAP_SMALL, SORT_CAP_MID, 512, 0>;
-  auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_MID, 0, 2048, 1>;
-  constexpr int smem_small = SORT_CAP_SMALL * 8, smem_mid = SORT_CAP_MID * 8, smem_big = SORT_CAP_BIG * 8;
+  // four launches, each owning a size class: tiny tiles (most of them: small CTAs, many per SM), tiles that fit 48 KB of
+  // shared memory, and the two crowded tiers drawn from the list the scan compiles
+  auto tiny = k_tile_sort<SORT_CAP_TINY, 0, SORT_CAP_TINY, 64, 0, true, SORT_THREADS_TINY>;
+  auto small = k_tile_sort<SORT_CAP_SMALL, SORT_CAP_TINY, SORT_CAP_SMALL, 512, 0, true, SORT_THREADS>;
+  auto mid = k_tile_sort<SORT_CAP_MID, SORT_CAP_SMALL, SORT_CAP_MID, 512, 0, false, SORT_THREADS>;
+  auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_MID, 0, 2048, 1, false, SORT_THREADS>;
+  constexpr int smem_tiny = SORT_CAP_TINY * 8, smem_small = SORT_CAP_SMALL * 8, smem_mid = SORT_CAP_MID * 8,
+                smem_big = SORT_CAP_BIG * 8;
   const DeviceInfo& di = device_info();
   if (!di.sort_attr_set) {  // once per device
     cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
@@ -405,6 +439,7 @@ void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t s
     cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
     di.sort_attr_set = true;
   }
+  launch_high_priority(tiny, dim3(T), dim3(SORT_THREADS_TINY), smem_tiny, st, g, im, b);
   launch_high_priority(small, dim3(T), dim3(SORT_THREADS), smem_small, st, g, im, b);
   launch_high_priority(mid, dim3(2 * di.sm_count), dim3(SORT_THREADS), smem_mid, st, g, im, b);  // two CTAs per SM draw the 6k-12k tiles
   launch_high_priority(big, dim3(di.sm_count), dim3(SORT_THREADS), smem_big, st, g, im, b);      // one CTA per SM draws the rest

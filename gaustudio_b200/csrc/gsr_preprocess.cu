@@ -27,11 +27,16 @@ __device__ const float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 
 struct V3 { float x, y, z; };
 
-// ---- TMA (cp.async.bulk) staging of a CTA's contiguous SH block: 256 Gaussians x (M-1) x 12 B of f_rest and
-// 256 x 12 B of f_dc land in shared memory while the threads do the projection math; rows of 3 / 45 words have
+// ---- TMA (cp.async.bulk) staging of a CTA's contiguous SH block: PRE_THREADS Gaussians x (M-1) x 12 B of f_rest and
+// PRE_THREADS x 12 B of f_dc land in shared memory while the threads do the projection math; rows of 3 / 45 words have
 // odd strides, so per-thread row reads are bank-conflict free.  The backward writes its SH gradients into the
 // same rows and ships the block with one bulk store per tensor.
-constexpr int PRE_THREADS = 256;
+// CTA size of the projection kernels: 128 measured best with several views in flight (64 / 128 / 256 in
+// profiles/r2_ab_block_sizes.json): smaller CTAs slot into the SMs as the compositing CTAs of other streams retire
+#ifndef GSR_PRE_THREADS
+#define GSR_PRE_THREADS 128
+#endif
+constexpr int PRE_THREADS = GSR_PRE_THREADS;
 constexpr int SH_ROW = 52;  // floats per staged row of the un-fused [P,16,3] tensor: 192 B of data + 16 B pad (16-B aligned rows)
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
@@ -239,7 +244,7 @@ __device__ __forceinline__ uint32_t tile_mask_of(float px, float py, float A, fl
 // ---------------------------------------------------------------------------------------------
 // K1: forward.cu:155-256
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PRE_THREADS, 4) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
+__global__ void __launch_bounds__(PRE_THREADS, 1024 / PRE_THREADS) k_preprocess_fwd(FwdArgs a, GeomView g, ImageView im) {
   extern __shared__ __align__(128) float sh_stage[];  // [256][3] f_dc rows, then [256][(M-1)*3] f_rest rows
   __shared__ __align__(8) unsigned long long sh_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;

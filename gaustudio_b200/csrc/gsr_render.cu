@@ -345,8 +345,11 @@ template <int NSUB> __device__ __forceinline__ int blk_ky(int w, int s) {
   return NSUB == 1 ? (w >> 1) : NSUB == 2 ? (w >> 1) * 2 + s : NSUB == 4 ? w * 2 + (s >> 1) : (s >> 1);
 }
 
+#ifndef GSR_BWD_BOUND_EXTRA
+#define GSR_BWD_BOUND_EXTRA 0
+#endif
 template <int NSUB, int MINB>
-__global__ void __launch_bounds__((NBLK / NSUB) * 32 + 32, MINB)
+__global__ void __launch_bounds__((NBLK / NSUB) * 32 + 32 + (NSUB == 1 ? GSR_BWD_BOUND_EXTRA : 0), MINB)
 k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, BinView bin,
              const float4* __restrict__ splat, float* __restrict__ grad, const float* __restrict__ dL_dpix,
              const float* __restrict__ dL_ddepthpix, const float* __restrict__ dL_dmedpix,
@@ -523,16 +526,28 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
 
 }  // namespace
 
+// Experiment knob (GSR_RENDER_PAD=<bytes>, read once): extra dynamic shared memory per compositing CTA.  It lowers the
+// number of compositing CTAs resident per SM so that CTAs of other streams' memory-bound kernels can co-reside.
+static size_t render_pad() {
+  static const size_t v = [] { const char* e = getenv("GSR_RENDER_PAD"); return e ? (size_t)atol(e) : (size_t)0; }();
+  return v;
+}
+template <typename K> static void allow_pad(K kernel) {
+  if (render_pad()) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_pad());
+}
+
 void launch_render_fwd(int W, int H, int gx, int gy, ImageView im, BinView b, GeomView g, const void* splat_tensor_map,
                        float* out_color, float* out_depth, float* out_median, float* out_opacity, cudaStream_t st) {
   if (splat_tensor_map) {
-    k_render_fwd<true><<<gx * gy, FWD_THREADS, 0, st>>>(W, H, gx, im, b, g.splat,
+    allow_pad(k_render_fwd<true>);
+    k_render_fwd<true><<<gx * gy, FWD_THREADS, render_pad(), st>>>(W, H, gx, im, b, g.splat,
                                                         *static_cast<const CUtensorMap*>(splat_tensor_map), out_color,
                                                         out_depth, out_median, out_opacity);
   } else {
     CUtensorMap none;
     memset(&none, 0, sizeof(none));
-    k_render_fwd<false><<<gx * gy, FWD_THREADS, 0, st>>>(W, H, gx, im, b, g.splat, none, out_color, out_depth, out_median,
+    allow_pad(k_render_fwd<false>);
+    k_render_fwd<false><<<gx * gy, FWD_THREADS, render_pad(), st>>>(W, H, gx, im, b, g.splat, none, out_color, out_depth, out_median,
                                                          out_opacity);
   }
 }
@@ -550,7 +565,8 @@ template <int NSUB, int MINB>
 static void launch_bwd(int W, int H, int gx, int gy, const float* bg, ImageView im, BinView b, GeomView g,
                        const float* dL_dpix, const float* dL_ddepth, const float* dL_dmedian, const float* dL_dopacity,
                        cudaStream_t st) {
-  k_render_bwd<NSUB, MINB><<<gx * gy, (NBLK / NSUB) * 32 + 32, 0, st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix,
+  allow_pad(k_render_bwd<NSUB, MINB>);
+  k_render_bwd<NSUB, MINB><<<gx * gy, (NBLK / NSUB) * 32 + 32, render_pad(), st>>>(W, H, gx, bg, im, b, g.splat, g.grad, dL_dpix,
                                                                        dL_ddepth, dL_dmedian, dL_dopacity);
 }
 
