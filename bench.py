@@ -598,6 +598,7 @@ def run_new(a):
             "note": "FP32/SFU-bound compositing: HBM fraction is low by construction (DESIGN.md, Roofline honesty)"}
     stages_out["_kernels_ms"] = {k: round(v, 4) for k, v in stage_ms.items()}
     stages_out["_workload"] = {"R": R, "R_binned": R_binned, "R_need": R_need, "P_visible": P_vis,
+                               "tile_instances_first_view": stats[0][4],
                                "depth2normal_ms": round(stage_ms["depth2normal"], 4)}
 
     per_step = KERNELS_FWD + (KERNELS_BWD if backward else 0)
@@ -659,14 +660,18 @@ def view_stats(_C, model, hc, dev, D, H, W, P, e):
         hc.full_proj_transform, math.tan(hc.FoVx * 0.5), math.tan(hc.FoVy * 0.5), H, W, model.get_features.contiguous(), D,
         hc.camera_center, False, False)
     if P is None:
-        return (R, 0, 0, 0)
+        return (R, 0, 0, 0, None)
     ex = _C.debug_export(P, W, H, R, gb, bb, ib)
     nc = ex["n_contrib"]
     Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
     pad = torch.zeros(Hp, Wp, dtype=nc.dtype, device=dev)
     pad[:H, :W] = nc
     r_need = int(pad.view(Hp // 16, 16, Wp // 16, 16).amax(dim=(1, 3)).sum())
-    return (R, r_need, int((radii > 0).sum()), ex["num_binned"])
+    n = (ex["ranges"][:, 1].long() - ex["ranges"][:, 0].long())
+    tiles = {"max": int(n.max()), "mean": round(float(n.float().mean()), 1),
+             "over_2048": int((n > 2048).sum()), "over_6144": int((n > 6144).sum()),
+             "over_12288": int((n > 12288).sum()), "over_26624": int((n > 26624).sum())}
+    return (R, r_need, int((radii > 0).sum()), ex["num_binned"], tiles)
 
 
 def run_dropin(a, _C, model, hcams, dev, renderers, step, K, Wn):

@@ -202,13 +202,14 @@ constexpr int SORT_THREADS = 512;
 #define GSR_SORT_THREADS_TINY 128
 #endif
 #ifndef GSR_SORT_CAP_TINY
-#define GSR_SORT_CAP_TINY 1024
+#define GSR_SORT_CAP_TINY 2048
 #endif
 constexpr int SORT_THREADS_TINY = GSR_SORT_THREADS_TINY;  // CTA size of the tier that owns the tiles with <= SORT_CAP_TINY instances
 constexpr int SORT_CAP_TINY = GSR_SORT_CAP_TINY;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-// Three launches cover every tile: a small-footprint kernel (one CTA per tile, 4 CTAs/SM) for tiles up to
-// SORT_CAP_SMALL entries, a two-CTAs-per-SM kernel for tiles up to SORT_CAP_MID and a one-CTA-per-SM kernel with
+// Four launches cover every tile: 128-thread CTAs (one per tile, ~13 per SM) for tiles up to SORT_CAP_TINY entries --
+// most tiles of a view, where a 512-thread CTA would mostly idle through the passes --, 512-thread CTAs (one per tile,
+// 4 CTAs/SM) up to SORT_CAP_SMALL, a two-CTAs-per-SM kernel up to SORT_CAP_MID and a one-CTA-per-SM kernel with
 // almost all of the SM's shared memory for the most crowded ones; only tiles beyond SORT_CAP_BIG entries fall back
 // to sorting in global memory (L2-resident scratch).  The two crowded tiers take their tiles from the compact list
 // the scan produced through an atomic ticket, so a CTA that drew a 25k-entry tile does not hold up a queue of others.
@@ -426,7 +427,7 @@ void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, c
 void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
   // four launches, each owning a size class: tiny tiles (most of them: small CTAs, many per SM), tiles that fit 48 KB of
   // shared memory, and the two crowded tiers drawn from the list the scan compiles
-  auto tiny = k_tile_sort<SORT_CAP_TINY, 0, SORT_CAP_TINY, 64, 0, true, SORT_THREADS_TINY>;
+  auto tiny = k_tile_sort<SORT_CAP_TINY, 0, SORT_CAP_TINY, SORT_CAP_TINY / 16, 0, true, SORT_THREADS_TINY>;
   auto small = k_tile_sort<SORT_CAP_SMALL, SORT_CAP_TINY, SORT_CAP_SMALL, 512, 0, true, SORT_THREADS>;
   auto mid = k_tile_sort<SORT_CAP_MID, SORT_CAP_SMALL, SORT_CAP_MID, 512, 0, false, SORT_THREADS>;
   auto big = k_tile_sort<SORT_CAP_BIG, SORT_CAP_MID, 0, 2048, 1, false, SORT_THREADS>;

@@ -245,6 +245,26 @@ def test_fused_activations_match_unfused():
     assert not errs, errs
 
 
+def test_fused_path_with_mostly_culled_ctas_matches_unfused():
+    """A view from inside the scene (BASELINE cfg 5 shape, most Gaussians culled): fused and un-fused renders agree
+    like they do on a fully visible scene."""
+    from gaustudio_b200 import renderers
+    from gaustudio_b200.synthetic import build_config
+    dev = torch.device("cuda")
+    imgs = {}
+    for fused in (False, True):
+        model, cams, _ = build_config("cfg5", P=40000, K=1, W=240, H=180)
+        model.to(dev)
+        r = renderers.make({"name": "vanilla_renderer", "fused_activations": fused})
+        with torch.no_grad():
+            out = r.render(cams[0].to(dev), model)
+        imgs[fused] = [out[k].cpu().numpy() for k in ("render", "rendered_depth", "rendered_final_opacity")]
+        vis = (out["radii"] > 0).float().mean().item()
+        assert 0.05 < vis < 0.7, vis
+    for a, b in zip(imgs[True], imgs[False]):
+        U.assert_images_close(a, b, atol=1e-4, outlier_frac=1e-3, what="fused image, sparse CTAs")
+
+
 def test_views_on_concurrent_streams_match_sequential():
     """The library enqueues on the caller's stream and keeps no global mutable state: independent views issued on
     different CUDA streams (what bench.py does) give the same images and gradients as one after the other."""

@@ -139,3 +139,29 @@ def test_medium_scene_bit_exact_and_sorted():
             ex, ref_driver.parse_binning(r[7], r[0]), ref_driver.parse_image_ranges(r[8], c["W"] * c["H"], T), c["W"], c["H"],
             c["P"])
         assert 0 < dropped < r[0] // 2 and ex["num_binned"] == r[0] - dropped
+
+
+def test_sparse_and_dense_projection_ctas_match_reference():
+    """A scene whose projection CTAs are a mix of dense ones (everything visible) and sparse ones (most Gaussians
+    behind the camera or far off screen, some off-screen centres whose splats still reach the image) stays
+    bit-identical to the compiled reference; gradients within 1e-3."""
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref/_refC.so not present")
+    s = dict(scenes.scene("D"))
+    rng = np.random.RandomState(21)
+    P = s["means3D"].shape[0]
+    xyz, sc = s["means3D"].copy(), s["scales"].copy()
+    far = np.arange(P) >= 1024
+    far &= rng.rand(P) < 0.7                 # the first 1024 stay as they are: dense CTAs
+    xyz[far] *= rng.uniform(3.0, 9.0, size=(int(far.sum()), 1)).astype(np.float32)   # behind the camera / off screen
+    big = np.where(far)[0][:40]
+    sc[big] = 1.5                            # off-screen centres whose splats still reach the image
+    s["means3D"], s["scales"] = xyz, sc
+    dev = torch.device("cuda")
+    new = scenes.run_torch(s, U.new_rasterize, dev)
+    ref = scenes.run_torch(s, U.ref_rasterize, dev)
+    assert 0.2 < (ref["radii"] > 0).mean() < 0.8
+    for k in FWD + ("radii",):
+        assert np.array_equal(new[k], ref[k]), f"{k} not bit-identical to the reference"
+    for k in _grad_keys(ref):
+        U.assert_grads_close(new[k], ref[k], what=f"sparse:{k}")

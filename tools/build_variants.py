@@ -15,8 +15,10 @@ VARIANTS = {
     "bwd48": ["-DGSR_BWD_BOUND_EXTRA=32"],
     "tiny64": ["-DGSR_SORT_THREADS_TINY=64"],
     "tiny256": ["-DGSR_SORT_THREADS_TINY=256"],
-    "tinycap512": ["-DGSR_SORT_CAP_TINY=512"],
-    "tinycap2048": ["-DGSR_SORT_CAP_TINY=2048"],
+    "tinycap1024": ["-DGSR_SORT_CAP_TINY=1024"],
+    "tinycap4096": ["-DGSR_SORT_CAP_TINY=4096"],
+    "tinycap4096_256": ["-DGSR_SORT_CAP_TINY=4096", "-DGSR_SORT_THREADS_TINY=256"],
+    "tinycap1536": ["-DGSR_SORT_CAP_TINY=1536"],
 }
 
 
