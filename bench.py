@@ -595,7 +595,10 @@ def run_new(a):
             "traffic_source": "constant from the committed ncu --set full capture (profiles/ncu_traffic.json), not "
                               "measured in this run",
             "peak_source": peak_src,
-            "note": "FP32/SFU-bound compositing: HBM fraction is low by construction (DESIGN.md, Roofline honesty)"}
+            "issue_active_pct": (traffic.get("_issue_active_pct") or {}).get(dom),
+            "note": "FP32/SFU-bound compositing: HBM fraction is low by construction (DESIGN.md, Roofline honesty); "
+                    "issue_active_pct = smsp__issue_active of this kernel in the committed ncu capture (a constant like "
+                    "`traffic`): the resource it is actually bound by"}
     stages_out["_kernels_ms"] = {k: round(v, 4) for k, v in stage_ms.items()}
     stages_out["_workload"] = {"R": R, "R_binned": R_binned, "R_need": R_need, "P_visible": P_vis,
                                "tile_instances_first_view": stats[0][4],

@@ -21,6 +21,7 @@ lines = [f"# ncu --set full summary ({tag})\n",
          "red_sectors / atom_sectors: L1->L2 write sectors of global reductions / returning atomics (the `lts__t_sectors_op_*` counters are not exposed by this ncu build)\n",
          "| kernel | " + " | ".join(c[1] for c in cols) + " | top stalls |", "|---|" + "---|" * (len(cols) + 1)]
 traffic = {}
+issue = {}
 for r in rows[2:]:
     name = r[idx["Kernel Name"]].split("::")[-1].split("(")[0]
     vals = []
@@ -40,6 +41,9 @@ for r in rows[2:]:
         return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(u, 1)
     base = name.split("<")[0]  # template instantiations of one kernel count together
     traffic[base] = traffic.get(base, 0.0) + mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+    ik = "smsp__issue_active.avg.pct_of_peak_sustained_active"
+    if ik in idx and base not in issue:
+        issue[base] = float(r[idx[ik]].replace(",", ""))
 open(os.path.join(out, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
 grp = {"preprocess_fwd": traffic.get("k_preprocess_fwd"), "render_fwd": traffic.get("k_render_fwd"), "render_bwd": traffic.get("k_render_bwd"),
        "preprocess_bwd": traffic.get("k_preprocess_bwd"),
@@ -50,6 +54,7 @@ tf = os.path.join(out, "ncu_traffic.json")
 if all(grp.values()):
     old = json.load(open(tf)) if os.path.exists(tf) else {}
     old.update(grp)
+    old["_issue_active_pct"] = {k[2:]: round(v, 1) for k, v in issue.items() if k in ("k_preprocess_fwd", "k_render_fwd", "k_render_bwd", "k_preprocess_bwd", "k_tile_sort", "k_scatter")}
     old["_note"] = f"bytes = dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, cfg3 view), from {os.path.basename(rep)}"
     json.dump(old, open(tf, "w"), indent=1)
 if launches:
