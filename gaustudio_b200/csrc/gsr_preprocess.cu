@@ -253,10 +253,6 @@ __global__ void __launch_bounds__(PRE_THREADS, 1024 / PRE_THREADS) k_preprocess_
   // whole CTA inside the array, coefficients beyond DC needed -> TMA staging
   const bool bulk = a.sh_bulk && a.D > 0 && (blockIdx.x + 1) * PRE_THREADS <= a.P;
   const int rest_row = (a.M - 1) * 3;
-#ifdef GSR_HOIST_POSITION  // experiment: issue the position loads before the staging barrier
-  V3 p = {0.f, 0.f, 0.f};
-  if (idx < a.P) p = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
-#endif
   if (bulk && threadIdx.x == 0) {
     const unsigned b_dc = PRE_THREADS * 3 * 4, b_rest = PRE_THREADS * rest_row * 4;
     bar_init_expect(&sh_bar, b_dc + b_rest);
@@ -275,9 +271,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 1024 / PRE_THREADS) k_preprocess_
   }
   if (idx < a.P) {
     int radius_i = 0;
-#ifndef GSR_HOIST_POSITION
     const V3 p = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
-#endif
     // in_frustum (auxiliary.h:139-164): only the near plane is tested
     const V3 p_view = xf4x3(p, a.view);
     if (p_view.z <= 0.2f) {

@@ -8,12 +8,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gaustudio_b200 import build as B  # noqa: E402
 
 VARIANTS = {
-    "hoistp": ["-DGSR_HOIST_POSITION"],
-    "hoistp_pre256": ["-DGSR_HOIST_POSITION", "-DGSR_PRE_THREADS=256"],
     "pre64": ["-DGSR_PRE_THREADS=64"],
     "pre256": ["-DGSR_PRE_THREADS=256"],
     "scatter128": ["-DGSR_SCATTER_THREADS=128"],
     "scatter512": ["-DGSR_SCATTER_THREADS=512"],
+    "bwdpred": ["-DGSR_BWD_PREDICATED=1"],
     "bwd48": ["-DGSR_BWD_BOUND_EXTRA=32"],
     "tiny64": ["-DGSR_SORT_THREADS_TINY=64"],
     "tiny256": ["-DGSR_SORT_THREADS_TINY=256"],

@@ -2,6 +2,7 @@
 un-fused and fused, so that everything compute-sanitizer reports comes from this library's kernels.
 Usage: compute-sanitizer --tool <tool> python tools/sanitize_driver.py"""
 import math
+import os
 import sys
 
 import torch
@@ -10,7 +11,10 @@ sys.path.insert(0, ".")
 from gaustudio_b200 import _C  # noqa: E402
 from gaustudio_b200.synthetic import build_config  # noqa: E402
 
-model, cams, c = build_config("cfg1", K=2)
+# SAN_SCENE="cfg2,150000,320,320": another named config / size (denser tiles: every sort tier and long compositing lists)
+_scene = os.environ.get("SAN_SCENE", "cfg1").split(",")
+_kw = dict(P=int(_scene[1]), W=int(_scene[2]), H=int(_scene[3])) if len(_scene) == 4 else {}
+model, cams, c = build_config(_scene[0], K=2, **_kw)
 dev = torch.device("cuda")
 model.to(dev)
 H, W, P = c["H"], c["W"], c["P"]
