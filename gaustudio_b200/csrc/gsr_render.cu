@@ -348,8 +348,9 @@ template <int NSUB> __device__ __forceinline__ int blk_ky(int w, int s) {
 #ifndef GSR_BWD_BOUND_EXTRA
 #define GSR_BWD_BOUND_EXTRA 0
 #endif
-#ifndef GSR_BWD_PREDICATED
-#define GSR_BWD_PREDICATED 0
+// 1 (default): the compositing backward evaluates exp with one ex2.approx; 0: precise expf (A/B: profiles/r2_ab_bwd_loop.json)
+#ifndef GSR_BWD_FASTEXP
+#define GSR_BWD_FASTEXP 1
 #endif
 template <int NSUB, int MINB>
 __global__ void __launch_bounds__((NBLK / NSUB) * 32 + 32 + (NSUB == 1 ? GSR_BWD_BOUND_EXTRA : 0), MINB)
@@ -387,7 +388,7 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
   const size_t HW = (size_t)W * H;
   const int lx = lane & 7, ly = lane >> 3;
   const int bx0 = tx * TILE_X, by0 = ty * TILE_Y;
-  float T[NSUB], Q[NSUB], g0[NSUB], g1[NSUB], g2[NSUB], gD[NSUB], gO[NSUB];
+  float T[NSUB], Q[NSUB], g0[NSUB], g1[NSUB], g2[NSUB], gD[NSUB], gO[NSUB], gM[NSUB];
   int lastc[NSUB], maxs[NSUB];
   int warp_max = 0;
 #pragma unroll
@@ -397,11 +398,12 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
     const size_t pid = (size_t)py * W + px;
     T[s] = inside ? im.final_T[pid] : 0.f;
     lastc[s] = inside ? (int)im.n_contrib[pid] : 0;
-    g0[s] = g1[s] = g2[s] = gD[s] = gO[s] = 0.f;
+    g0[s] = g1[s] = g2[s] = gD[s] = gO[s] = gM[s] = 0.f;
     if (inside) {
       g0[s] = dL_dpix[pid]; g1[s] = dL_dpix[HW + pid]; g2[s] = dL_dpix[2 * HW + pid];
       gD[s] = dL_ddepthpix[pid];
       gO[s] = dL_dopacpix[pid];
+      gM[s] = dL_dmedpix[pid];  // channel 0 of the median-depth gradient (quirk 4)
     }
     // Q = (sum of s_i w_i over the contributors behind the current one) + T_final * (bg . dL_dpix): the second
     // term is the background contribution of backward.cu:584-587, folded into the same recurrence
@@ -414,12 +416,10 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
   // which lane publishes which reduced component (see the butterfly below)
   const bool pub = ((lane & 3) == 0) || lane == 1 || lane == 17;
   const int slot = ((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9);
-#if GSR_BWD_PREDICATED
   // kept opaque so that the compiler holds them in registers instead of rebuilding them from %tid for every pair
   unsigned lanebits = (unsigned)lane | (pub ? 32u : 0u);
   float* gslot = grad + slot;
   asm volatile("" : "+r"(lanebits), "+l"(gslot));
-#endif
 
   for (int b = 0; b < nb; b++) {
     const int st = b % NSTAGE;
@@ -454,13 +454,9 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
           const float4* rec = sb + jj * SPLAT_F4;
           const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
           // v0-2 colour, v3 depth, v4 opacity, v5-6 sum u dx / u dy, v7-9 sum u dx^2 / u dx dy / u dy^2
-#if GSR_BWD_PREDICATED
           // (one pixel per lane: every component is assigned before it is read, see `acc` below)
           float v0, v1, v2, v3, v4, v5, v6, v7, v8, v9;
           if (NSUB > 1) v0 = v1 = v2 = v3 = v4 = v5 = v6 = v7 = v8 = v9 = 0.f;
-#else
-          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
-#endif
           bool contrib = false;
 #pragma unroll
           for (int s = 0; s < NSUB; s++) {
@@ -471,19 +467,27 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
             const float t2 = __fmul_rn(dx, q0.z);
             const float t3 = __fmul_rn(__fmul_rn(dx, q0.w), dy);
             const float power = __fmaf_rn(__fmaf_rn(dx, t2, t1), -0.5f, -t3);
-#if GSR_BWD_PREDICATED
             // branch-free form: a lane whose pixel does not take this Gaussian (backward.cu:520-537: at or beyond
             // n_contrib, power > 0, alpha < 1/255) runs the same arithmetic with G = 0, which makes its alpha, weight
             // and every accumulated term exactly zero and leaves its T and Q untouched (1 / (1 - 0) == 1 exactly)
             // one pixel per lane: the sums start here, so plain products (no zero-initialised accumulators)
             auto acc = [](float x, float y, float z) { return NSUB == 1 ? x * y : fmaf(x, y, z); };
+#if GSR_BWD_FASTEXP
+            // exp as ONE ex2.approx of power * log2(e) (2 instructions instead of expf's 10; relative error ~4e-7 for
+            // the powers that pass the alpha test: gradient tolerance is 1e-3).  A pair whose alpha sits within that
+            // error of 1/255 may be taken here and skipped by the forward (or the reverse): one 0.4 % step of one
+            // pixel's transmittance
+            float G0;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G0) : "f"(power * 1.4426950408889634f));
+#else
             const float G0 = expf(power);
-            const float a0 = fminf(0.99f, q1.y * G0);
-            const bool valid = (pos < lastc[s]) && !(power > 0.0f) && !(a0 < 1.0f / 255.0f);
+#endif
+            const float al0 = fminf(0.99f, q1.y * G0);
+            const bool valid = (pos < lastc[s]) && !(power > 0.0f) && !(al0 < 1.0f / 255.0f);
             if (!__any_sync(FULL, valid)) continue;
             contrib = true;
             const float G = valid ? G0 : 0.f;
-            const float alpha = valid ? a0 : 0.f;
+            const float alpha = valid ? al0 : 0.f;
             float inv;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
             const float Tb = T[s] * inv;
@@ -495,10 +499,9 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
             v1 = acc(w, g1[s], v1);
             v2 = acc(w, g2[s], v2);
             v3 = acc(w, gD[s], v3);
-            if (Tb > 0.5f && T[s] < 0.5f) {  // backward.cu:566-569 (never true for a masked lane: Tb == T there)
-              const int px = bx0 + blk_kx<NSUB>(warp, s) * 8 + lx, py = by0 + blk_ky<NSUB>(warp, s) * 4 + ly;
-              v3 += dL_dmedpix[(size_t)py * W + px];
-            }
+            // backward.cu:566-569: the Gaussian at which T crosses 0.5 also receives the median-depth gradient
+            // (never true for a masked lane: Tb == T there)
+            if (Tb > 0.5f && T[s] < 0.5f) v3 += gM[s];
             v4 = acc(w, gO[s], v4);
             v4 = fmaf(G, dL_dalpha, v4);
             const float u = (q1.y * dL_dalpha) * G;
@@ -510,52 +513,9 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
             v9 = acc(uy, dy, v9);
             T[s] = Tb;
           }
-#else
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, q1.y * G);
-            // backward.cu:520-537: entries at or beyond n_contrib, power > 0 and alpha < 1/255 are skipped
-            const bool valid = (pos < lastc[s]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!__any_sync(FULL, valid)) continue;
-            contrib = true;
-            if (valid) {
-              float inv;  // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: one MUFU.RCP (gradient tolerance 1e-3)
-              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
-              const float Tb = T[s] * inv;  // transmittance in front of this Gaussian
-              const float w = alpha * Tb;   // its blending weight
-              // s = <this Gaussian's blended channels, the pixel's incoming gradient> (colour, depth, coverage = 1);
-              // dL/dalpha = s Tb - (sum behind of s_i w_i + bg term) / (1 - alpha)   [backward.cu:544-587 regrouped:
-              // (c - accum_rec) T == c T - (sum behind of c_i w_i) / (1 - alpha)]
-              const float sj = fmaf(q1.w, g0[s], fmaf(q2.x, g1[s], fmaf(q2.y, g2[s], fmaf(q1.z, gD[s], gO[s]))));
-              const float dL_dalpha = fmaf(sj, Tb, -(Q[s] * inv));
-              Q[s] = fmaf(sj, w, Q[s]);
-              v0 = fmaf(w, g0[s], v0);
-              v1 = fmaf(w, g1[s], v1);
-              v2 = fmaf(w, g2[s], v2);
-              v3 = fmaf(w, gD[s], v3);
-              if (Tb > 0.5f && T[s] < 0.5f) {  // backward.cu:566-569: channel 0 of the median grad only (quirk 4)
-                const int px = bx0 + blk_kx<NSUB>(warp, s) * 8 + lx, py = by0 + blk_ky<NSUB>(warp, s) * 4 + ly;
-                v3 += dL_dmedpix[(size_t)py * W + px];
-              }
-              v4 = fmaf(w, gO[s], v4);          // direct term, backward.cu:575 (quirk 5)
-              v4 = fmaf(G, dL_dalpha, v4);      // through alpha = o G
-              const float u = (q1.y * dL_dalpha) * G;  // dL/dG * G
-              const float ux = u * dx, uy = u * dy;
-              v5 += ux;
-              v6 += uy;
-              v7 = fmaf(ux, dx, v7);
-              v8 = fmaf(ux, dy, v8);
-              v9 = fmaf(uy, dy, v9);
-              T[s] = Tb;
-            }
-          }
-#endif
           if (!contrib) continue;
           // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
-#if GSR_BWD_PREDICATED
           const bool h16 = lanebits & 16, h8 = lanebits & 8, h4 = lanebits & 4;
-#else
-          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-#endif
           float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
           a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
           a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
@@ -575,16 +535,12 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
           e += __shfl_xor_sync(FULL, e, 4);
           e += __shfl_xor_sync(FULL, e, 2);
           e += __shfl_xor_sync(FULL, e, 1);
-#if GSR_BWD_PREDICATED
           {  // two predicated reductions instead of a select + one: the select's predicate would be rebuilt from tid
             float* gp = gslot + (size_t)__float_as_int(q2.z) * GRAD_F;
             // (red.global spelled out: behind the opaque pointer atomicAdd would take the generic-address path)
             if ((lanebits & 3) == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp), "f"(c) : "memory");
             else if (lanebits & 32) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp), "f"(e) : "memory");
           }
-#else
-          if (pub) atomicAdd(grad + (size_t)__float_as_int(q2.z) * GRAD_F + slot, ((lane & 3) == 0) ? c : e);
-#endif
         }
       }
     }

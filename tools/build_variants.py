@@ -12,7 +12,7 @@ VARIANTS = {
     "pre256": ["-DGSR_PRE_THREADS=256"],
     "scatter128": ["-DGSR_SCATTER_THREADS=128"],
     "scatter512": ["-DGSR_SCATTER_THREADS=512"],
-    "bwdpred": ["-DGSR_BWD_PREDICATED=1"],
+    "exactexp": ["-DGSR_BWD_FASTEXP=0"],
     "bwd48": ["-DGSR_BWD_BOUND_EXTRA=32"],
     "tiny64": ["-DGSR_SORT_THREADS_TINY=64"],
     "tiny256": ["-DGSR_SORT_THREADS_TINY=256"],

@@ -60,7 +60,7 @@ L.append("```\n")
 # per-pair loop of the compositing backward: from the first LDS.128 of a record to the loop's back edge
 for k, ins in kern.items():
     if k.startswith("k_render_bwd<1"):
-        red = next(i for i, s in enumerate(ins) if "REDG" in s)
+        red = max(i for i, s in enumerate(ins) if "REDG" in s)  # the last of the (two, predicated) reductions
         first = max(i for i, s in enumerate(ins[:red]) if s.startswith("UBREV"))  # __ffs of the survivor mask: top of the loop
         L.append(f"`{k}`: the per-(8x4 block, Gaussian) pair loop spans {red - first + 1} instructions from the survivor mask's "
                  f"`__ffs` to the `REDG` ({sum('SHFL' in s for s in ins[first:red])} SHFL, "
