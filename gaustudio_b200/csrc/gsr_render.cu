@@ -413,9 +413,10 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
     maxs[s] = (int)__reduce_max_sync(FULL, (unsigned)lastc[s]);
     warp_max = max(warp_max, maxs[s]);
   }
-  // which lane publishes which reduced component (see the butterfly below)
-  const bool pub = ((lane & 3) == 0) || lane == 1 || lane == 17;
-  const int slot = ((lane & 3) == 0) ? (lane >> 2) : (lane == 1 ? 8 : 9);
+  // which lane publishes which reduced component (see the butterfly below): even lanes; of those with bit 1 set (they
+  // all hold component 4 / 9) only lanes 2 and 18
+  const bool pub = (lane & 1) == 0 && ((lane & 2) == 0 || (lane & 12) == 0);
+  const int slot = ((lane & 16) ? 5 : 0) + ((lane & 2) ? 4 : ((lane & 4) ? 2 : 0) + ((lane & 8) ? 1 : 0));
   // kept opaque so that the compiler holds them in registers instead of rebuilding them from %tid for every pair
   unsigned lanebits = (unsigned)lane | (pub ? 32u : 0u);
   float* gslot = grad + slot;
@@ -514,33 +515,30 @@ k_render_bwd(int W, int H, int gx, const float* __restrict__ bg, ImageView im, B
             T[s] = Tb;
           }
           if (!contrib) continue;
-          // transposed butterfly: 8 components -> lanes 4c hold the total of component c (c = lane>>2)
-          const bool h16 = lanebits & 16, h8 = lanebits & 8, h4 = lanebits & 4;
-          float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
-          a0 += __shfl_xor_sync(FULL, h16 ? v0 : v4, 16);
-          a1 += __shfl_xor_sync(FULL, h16 ? v1 : v5, 16);
-          a2 += __shfl_xor_sync(FULL, h16 ? v2 : v6, 16);
-          a3 += __shfl_xor_sync(FULL, h16 ? v3 : v7, 16);
-          float b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
-          b0 += __shfl_xor_sync(FULL, h8 ? a0 : a2, 8);
-          b1 += __shfl_xor_sync(FULL, h8 ? a1 : a3, 8);
-          float c = h4 ? b1 : b0;
-          c += __shfl_xor_sync(FULL, h4 ? b0 : b1, 4);
-          c += __shfl_xor_sync(FULL, c, 2);
-          c += __shfl_xor_sync(FULL, c, 1);
-          // the remaining two components: lanes < 16 end with v8's total, lanes >= 16 with v9's
-          float e = h16 ? v9 : v8;
-          e += __shfl_xor_sync(FULL, h16 ? v8 : v9, 16);
-          e += __shfl_xor_sync(FULL, e, 8);
-          e += __shfl_xor_sync(FULL, e, 4);
-          e += __shfl_xor_sync(FULL, e, 2);
-          e += __shfl_xor_sync(FULL, e, 1);
-          {  // two predicated reductions instead of a select + one: the select's predicate would be rebuilt from tid
-            float* gp = gslot + (size_t)__float_as_int(q2.z) * GRAD_F;
-            // (red.global spelled out: behind the opaque pointer atomicAdd would take the generic-address path)
-            if ((lanebits & 3) == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp), "f"(c) : "memory");
-            else if (lanebits & 32) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp), "f"(e) : "memory");
-          }
+          // transposed butterfly over all ten components: every stage halves what a lane still carries (two of its
+          // values form one, the partner lane keeps the other half), an odd one out is reduced in place --
+          // 5 + 3 + 2 + 1 + 1 = 12 shuffles -- and one lane per component ends up with its total in ONE register:
+          //   bit 16 of the lane picks v0-4 / v5-9, then bit 1 = 0: component 2*bit2 + bit3, bit 1 = 1: component 4
+          const bool h16 = lanebits & 16, h8 = lanebits & 8, h4 = lanebits & 4, h2 = lanebits & 2;
+          float x0 = h16 ? v5 : v0, x1 = h16 ? v6 : v1, x2 = h16 ? v7 : v2, x3 = h16 ? v8 : v3, x4 = h16 ? v9 : v4;
+          x0 += __shfl_xor_sync(FULL, h16 ? v0 : v5, 16);
+          x1 += __shfl_xor_sync(FULL, h16 ? v1 : v6, 16);
+          x2 += __shfl_xor_sync(FULL, h16 ? v2 : v7, 16);
+          x3 += __shfl_xor_sync(FULL, h16 ? v3 : v8, 16);
+          x4 += __shfl_xor_sync(FULL, h16 ? v4 : v9, 16);
+          float y0 = h8 ? x1 : x0, y1 = h8 ? x3 : x2;
+          y0 += __shfl_xor_sync(FULL, h8 ? x0 : x1, 8);
+          y1 += __shfl_xor_sync(FULL, h8 ? x2 : x3, 8);
+          x4 += __shfl_xor_sync(FULL, x4, 8);
+          float z0 = h4 ? y1 : y0;
+          z0 += __shfl_xor_sync(FULL, h4 ? y0 : y1, 4);
+          x4 += __shfl_xor_sync(FULL, x4, 4);
+          float r = h2 ? x4 : z0;
+          r += __shfl_xor_sync(FULL, h2 ? z0 : x4, 2);
+          r += __shfl_xor_sync(FULL, r, 1);
+          // (red.global spelled out: behind the opaque pointer atomicAdd would take the generic-address path)
+          if (lanebits & 32)
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gslot + (size_t)__float_as_int(q2.z) * GRAD_F), "f"(r) : "memory");
         }
       }
     }
