@@ -11,4 +11,4 @@ timeout -k 10 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpur
 timeout -k 10 600 python bench.py --config cfg5 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_final2_bench_cfg5.json 2> gpurun_out/r2_final2_bench_cfg5.err
 timeout -k 10 600 python bench.py --train 1 --steps 20 --warmup 6 > gpurun_out/r2_final2_train_1gpu.json 2> gpurun_out/r2_final2_train_1gpu.err
 tail -c 600 gpurun_out/r2_final2_bench_new.json
-rm -f gpurun_out/r2_blk_*; bash tools/block_size_ab.sh scatter_occ8 > gpurun_out/r2_scatter_occ_ab.txt 2>&1; tail -5 gpurun_out/r2_scatter_occ_ab.txt
+
