@@ -58,6 +58,22 @@ def set_tile_order(mode):
     return int(_lib.lib().gsr_set_tile_order(int(mode)))
 
 
+def set_speculation(on):
+    """Exact-mode speculation of the forward (gsr_set_speculation): True (default) sizes the binning buffer from the
+    previous view's count and enqueues the whole forward before blocking on the count read; False is the plain blocking
+    read in the middle of the forward; None restores the default.  Process-wide; returns the previous setting
+    (None = default).  Results and the returned num_rendered are identical either way."""
+    prev = int(_lib.lib().gsr_set_speculation(-1 if on is None else int(bool(on))))
+    return None if prev < 0 else bool(prev)
+
+
+def speculation_stats():
+    """(hits, redos): exact-mode forwards whose capacity guess held / that had to re-bin with the exact count."""
+    h, r = C.c_int64(0), C.c_int64(0)
+    _lib.lib().gsr_speculation_stats(C.byref(h), C.byref(r))
+    return int(h.value), int(r.value)
+
+
 def last_num_binned():
     """Tile instances the most recent EXACT-mode forward on this thread actually binned.  The returned `num_rendered`
     keeps the reference's meaning (sum of the tile-rect areas); (Gaussian, tile) pairs that cannot reach alpha >= 1/255

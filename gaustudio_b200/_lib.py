@@ -37,6 +37,8 @@ SIGNATURES = {
     "gsr_knn_grid": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "gsr_adam_step": (_I, [_I, _P, C.c_double, C.c_double, C.c_double, _L, _I, _F, _I, _P]),
     "gsr_set_tile_order": (_I, [_I]),
+    "gsr_set_speculation": (_I, [_I]),
+    "gsr_speculation_stats": (_I, [_P, _P]),
     "gsr_profile_enable": (_I, [_I]),
     "gsr_profile_read": (_I, [_P, _P]),
     "gsr_debug_export": (_I, [_I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

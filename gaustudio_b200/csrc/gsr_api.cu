@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -75,6 +76,19 @@ int high_priority() {
     return cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess ? greatest : 0;
   }();
   return prio;
+}
+
+void apply_carveout(const void* kernel) {
+  static const int pref = [] { const char* e = getenv("GSR_CARVEOUT"); return (e && *e) ? atoi(e) : -1; }();
+  if (pref < 0) return;
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void*>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> l(mu);
+  for (auto& s : seen) if (s.first == dev && s.second == kernel) return;
+  seen.emplace_back(dev, kernel);
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pref > 100 ? 100 : pref) != cudaSuccess) cudaGetLastError();
 }
 
 const DeviceInfo& device_info() {
@@ -185,6 +199,66 @@ inline char* aligned_base(char* p) { return reinterpret_cast<char*>(align_up(rei
 __global__ void k_init_header(ImageHeader* h, unsigned long long cap) {
   h->num_rendered = 0;
   h->num_rect = 0;
+  h->capacity = cap;
+  h->overflow = 0;
+  h->num_big = 0;
+  h->ticket[0] = 0;
+  h->ticket[1] = 0;
+}
+
+// ---- speculative exact forward -------------------------------------------------------------------------------------
+// Exact mode has to read the binned instance count back before it can size the binning buffer (the reference does the
+// same, rasterizer_impl.cu:284), and a blocking read in the MIDDLE of the forward leaves the GPU idle while the host
+// wakes up, allocates and launches the second half.  The count of a view is close to the count of the previous view of
+// the same (device, P, W, H), so from the second view on the forward sizes the binning buffer for 1.25 x the last count,
+// enqueues scatter / sort / compositing right behind the scan and only THEN blocks on the count (an event recorded
+// after its copy, not the whole stream).  If the guess was large enough -- the normal case -- nothing else happens: the
+// returned num_rendered is exact and the results are the same kernels on the same data.  If it was too small the kernels
+// have dropped the overflowing tiles (never an out-of-bounds write); the scan is repeated with the exact capacity and the
+// second half runs again.  GSR_SPECULATE=0 / gsr_set_speculation(0): always the plain blocking form.  debug=1: plain form.
+std::atomic<int> g_speculate{-1};
+std::atomic<long long> g_spec_hits{0}, g_spec_redos{0};
+bool speculate_enabled() {
+  static const int dflt = [] { const char* e = getenv("GSR_SPECULATE"); return (e && e[0] == '0') ? 0 : 1; }();
+  const int v = g_speculate.load(std::memory_order_relaxed);
+  return (v >= 0 ? v : dflt) != 0;
+}
+struct SpecHint { int dev, P, W, H; long long binned; };
+std::mutex g_hint_mu;
+SpecHint g_hints[16];
+int g_hint_n = 0, g_hint_next = 0;
+long long hint_get(int dev, int P, int W, int H) {
+  std::lock_guard<std::mutex> l(g_hint_mu);
+  for (int i = 0; i < g_hint_n; i++)
+    if (g_hints[i].dev == dev && g_hints[i].P == P && g_hints[i].W == W && g_hints[i].H == H) return g_hints[i].binned;
+  return -1;
+}
+void hint_put(int dev, int P, int W, int H, long long binned) {
+  std::lock_guard<std::mutex> l(g_hint_mu);
+  for (int i = 0; i < g_hint_n; i++)
+    if (g_hints[i].dev == dev && g_hints[i].P == P && g_hints[i].W == W && g_hints[i].H == H) { g_hints[i].binned = binned; return; }
+  const int slot = g_hint_n < 16 ? g_hint_n++ : (g_hint_next++ & 15);
+  g_hints[slot] = {dev, P, W, H, binned};
+}
+// per host thread: 16 pinned bytes for the two counts and the event the host blocks on (re-made when the device changes)
+struct SpecHost {
+  long long* counts = nullptr;
+  cudaEvent_t ev = nullptr;
+  int dev = -1;
+  bool ready(int d) {
+    if (dev == d && counts && ev) return true;
+    if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+    if (!counts && cudaHostAlloc(reinterpret_cast<void**>(&counts), 16, cudaHostAllocDefault) != cudaSuccess) { counts = nullptr; cudaGetLastError(); return false; }
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; cudaGetLastError(); return false; }
+    dev = d;
+    return true;
+  }
+};
+thread_local SpecHost t_spec;
+// capacity for a view whose predecessor needed `binned` instances (the carve rounds the arrays up to 1 Mi entries anyway)
+inline long long spec_capacity(long long binned) { return binned + binned / 4 + 4096; }
+
+__global__ void k_set_capacity(ImageHeader* h, unsigned long long cap) {
   h->capacity = cap;
   h->overflow = 0;
   h->num_big = 0;
@@ -338,7 +412,14 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
   a.sh_bulk = fused && M > 1 && ((reinterpret_cast<size_t>(f_dc) | reinterpret_cast<size_t>(f_rest)) & 15) == 0;
   a.sh_rows = !fused && shs && M == 16 && (reinterpret_cast<size_t>(shs) & 15) == 0;
 
-  const unsigned long long cap0 = r_capacity > 0 ? (unsigned long long)r_capacity : ~0ull;
+  // exact mode, from the second view of a shape on: speculate on the binning capacity (see above)
+  int dev = 0;
+  long long spec_cap = 0;
+  if (r_capacity <= 0 && !dbg && speculate_enabled() && cudaGetDevice(&dev) == cudaSuccess) {
+    const long long h = hint_get(dev, P, width, height);
+    if (h >= 0 && t_spec.ready(dev)) spec_cap = spec_capacity(h);
+  }
+  const unsigned long long cap0 = r_capacity > 0 ? (unsigned long long)r_capacity : (spec_cap > 0 ? (unsigned long long)spec_cap : ~0ull);
   if (!check(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * T * SUBBINS, st), "memset tile_count")) return -1;
   launch_high_priority(k_init_header, dim3(1), dim3(1), 0, st, im.hdr, (unsigned long long)cap0);
   { Prof pf(0, st); launch_preprocess_fwd(a, g, im, st); }
@@ -346,12 +427,51 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
   { Prof pf(1, st); launch_tile_scan(im, T, st); }
   if (!stage_ok(dbg, st, "tile_scan")) return -1;
 
+  // second half of the forward for a given binning capacity: scatter, per-tile sort, compositing
+  auto second_half = [&](long long cap) -> bool {
+    char* bbuf = binning_alloc(binning_user, binning_bytes(cap));
+    if (!bbuf) { g_err = "gsr_forward: binning allocation failed"; return false; }
+    BinView b = carve_binning(aligned_base(bbuf), cap);
+    if (cap > 0) {
+      { Prof pf(2, st); launch_scatter(P, gx, T, g, im, b, st); }
+      if (!stage_ok(dbg, st, "scatter")) return false;
+      { Prof pf(3, st); launch_tile_sort(T, g, im, b, st); }
+      if (!stage_ok(dbg, st, "tile_sort")) return false;
+    }
+    CUtensorMap tmap;
+    const bool use_tma = fwd_tma_enabled() && encode_splat_map(&tmap, g.splat, P);
+    { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, g, use_tma ? &tmap : nullptr, out_color, out_depth, out_median_depth, out_opacity, st); }
+    return stage_ok(dbg, st, "render_fwd");
+  };
+
   // Two counts: `binned` = tile instances that survive the exact tile culling (sizes the binning buffer) and the
   // reference's num_rendered = sum of the rect areas (what the API returns in exact mode).
   long long cap, ret;
   if (r_capacity > 0) {
     cap = ret = r_capacity;
     if (r_host && !check(cudaMemcpyAsync(r_host, &im.hdr->num_rendered, 8, cudaMemcpyDeviceToHost, st), "async R")) return -1;
+  } else if (spec_cap > 0) {
+    // speculative exact mode: the second half is already enqueued when the host blocks on the counts
+    long long* counts = t_spec.counts;
+    if (!check(cudaMemcpyAsync(counts, &im.hdr->num_rendered, 16, cudaMemcpyDeviceToHost, st), "read R")) return -1;
+    if (!check(cudaEventRecord(t_spec.ev, st), "read R (event)")) return -1;
+    if (!second_half(spec_cap)) return -1;
+    if (!check(cudaEventSynchronize(t_spec.ev), "read R (sync)")) return -1;
+    const long long binned = counts[0];
+    ret = counts[1];
+    if (r_host) *r_host = binned;
+    hint_put(dev, P, width, height, binned);
+    if (binned <= spec_cap) {
+      g_spec_hits.fetch_add(1, std::memory_order_relaxed);
+      return ret;
+    }
+    // the guess was too small: redo the scan with the exact capacity, then the second half once more (stream order
+    // keeps the abandoned launches, which only touched their own smaller buffer, ahead of the new ones)
+    g_spec_redos.fetch_add(1, std::memory_order_relaxed);
+    k_set_capacity<<<1, 1, 0, st>>>(im.hdr, (unsigned long long)binned);
+    { Prof pf(1, st); launch_tile_scan(im, T, st); }
+    if (!stage_ok(dbg, st, "tile_scan (redo)")) return -1;
+    cap = binned;
   } else {
     // exact mode: the one blocking read the reference also performs (rasterizer_impl.cu:284)
     long long counts[2] = {0, 0};  // {binned, rect-sum}: adjacent header fields
@@ -360,21 +480,9 @@ static int64_t forward_impl(int fused, const float* f_dc, const float* f_rest, g
     if (r_host) *r_host = counts[0];
     cap = counts[0];
     ret = counts[1];
+    if (!dbg && cudaGetDevice(&dev) == cudaSuccess) hint_put(dev, P, width, height, cap);
   }
-  char* bbuf = binning_alloc(binning_user, binning_bytes(cap));
-  if (!bbuf) { g_err = "gsr_forward: binning allocation failed"; return -1; }
-  BinView b = carve_binning(aligned_base(bbuf), cap);
-
-  if (cap > 0) {
-    { Prof pf(2, st); launch_scatter(P, gx, T, g, im, b, st); }
-    if (!stage_ok(dbg, st, "scatter")) return -1;
-    { Prof pf(3, st); launch_tile_sort(T, g, im, b, st); }
-    if (!stage_ok(dbg, st, "tile_sort")) return -1;
-  }
-  CUtensorMap tmap;
-  const bool use_tma = fwd_tma_enabled() && encode_splat_map(&tmap, g.splat, P);
-  { Prof pf(4, st); launch_render_fwd(width, height, gx, gy, im, b, g, use_tma ? &tmap : nullptr, out_color, out_depth, out_median_depth, out_opacity, st); }
-  if (!stage_ok(dbg, st, "render_fwd")) return -1;
+  if (!second_half(cap)) return -1;
   return ret;
 }
 
@@ -601,6 +709,14 @@ int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_b
 }
 
 int gsr_set_tile_order(int mode) { return set_tile_order(mode); }
+
+int gsr_set_speculation(int on) { return g_speculate.exchange(on < 0 ? -1 : (on != 0)); }
+
+int gsr_speculation_stats(int64_t* hits, int64_t* redos) {
+  if (hits) *hits = g_spec_hits.load();
+  if (redos) *redos = g_spec_redos.load();
+  return 0;
+}
 
 int gsr_profile_enable(int on) {
   g_prof_on = on != 0;

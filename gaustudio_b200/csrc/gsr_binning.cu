@@ -21,6 +21,8 @@
 #include "gsr_internal.cuh"
 #include <atomic>
 #include <cstdlib>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 
 namespace gsr {
@@ -127,6 +129,129 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T,
   for (int t = tid; t < T; t += SCAN_THREADS) {
     const unsigned pos = atomicAdd(&cls_start[size_class(t)], 1u);
     im.tile_order[longest_first == 2 ? (unsigned)T - 1u - pos : pos] = (uint32_t)t;  // 2: shortest first
+  }
+}
+
+// ---- level 1a, cluster form (default): the same scan by a thread-block cluster of 8 CTAs ---------------------------
+// The single-CTA scan is pure latency on one SM (37 us at 1080p: 8160 tiles x 16 counters through one SM's load path,
+// twice, plus a counting sort with contended shared-memory atomics).  Here every thread owns ONE tile per round (a round
+// = 8 x 1024 tiles: a 1080p image is one round), its 16 counters stay in registers between the total and the cursor
+// pass, the 8 CTAs exchange their round totals through distributed shared memory (one cluster barrier per round), and
+// the size-class counting sort of the launch order uses warp-aggregated atomics and a cluster-wide class histogram.
+// Same outputs as k_tile_scan except for the (free) order of tiles inside a size class and of the crowded-tile list.
+constexpr int SCAN_CLUSTER = 8;
+#ifndef GSR_SCAN_CL_THREADS
+#define GSR_SCAN_CL_THREADS 512
+#endif
+constexpr int SCAN_CL_THREADS = GSR_SCAN_CL_THREADS;  // 512: a 1080p image is two rounds; half an SM's threads per CTA,
+                                                      // so the cluster finds room next to other views' kernels sooner
+static_assert(SCAN_CL_THREADS % 64 == 0 && SCAN_CL_THREADS >= 64 && SCAN_CL_THREADS <= 1024, "cluster scan CTA size");
+__global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SCAN_CL_THREADS)
+k_tile_scan_cluster(ImageView im, int T, int longest_first) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned cta_total[2];  // this CTA's total of the round, double-buffered by round parity
+  __shared__ unsigned cls_count[64], cls_start[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long cap = im.hdr->capacity;
+  unsigned long long carry = 0;  // tiles of earlier rounds (the same value in every CTA)
+  constexpr int ROUND = SCAN_CLUSTER * SCAN_CL_THREADS;
+  int round = 0;
+  for (int t0 = 0; t0 < T; t0 += ROUND, round++) {
+    const int t = t0 + (int)rank * SCAN_CL_THREADS + tid;
+    unsigned cnt[SUBBINS], c = 0;
+#pragma unroll
+    for (int s = 0; s < SUBBINS; s++) { cnt[s] = t < T ? im.tile_count[s * T + t] : 0u; c += cnt[s]; }
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+    __syncthreads();  // warp_sums of the previous round are consumed
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    unsigned wv = lane < SCAN_CL_THREADS / 32 ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, wv, o); if (lane >= o) wv += u; }
+    const unsigned my_total = __shfl_sync(FULL, wv, 31);
+    const unsigned before_warp = __shfl_sync(FULL, wv, max(warp - 1, 0));
+    const unsigned excl = (warp ? before_warp : 0u) + (incl - c);  // exclusive prefix inside this CTA's tiles of the round
+    if (tid == 0) cta_total[round & 1] = my_total;
+    cluster.sync();  // every CTA's total of this round is published
+    unsigned before = 0, all = 0;
+#pragma unroll
+    for (unsigned r = 0; r < (unsigned)SCAN_CLUSTER; r++) {
+      const unsigned v = *cluster.map_shared_rank(&cta_total[round & 1], r);
+      before += r < rank ? v : 0u;
+      all += v;
+    }
+    if (t < T) {
+      unsigned long long at = carry + before + excl;
+      // tiles whose segment does not fit the binning capacity render nothing (pipelined-mode overflow)
+      const bool fits = at + c <= cap;
+      im.tile_range[t] = (c && fits) ? make_uint2((unsigned)at, (unsigned)(at + c)) : make_uint2(0u, 0u);
+      if (fits && c > (unsigned)SORT_CAP_SMALL_) im.big_tiles[atomicAdd(&im.hdr->num_big, 1u)] = (unsigned)t;
+#pragma unroll
+      for (int s = 0; s < SUBBINS; s++) {
+        im.tile_cursor[s * T + t] = fits ? (unsigned)at : 0x80000000u;  // dropped: slots fail the range test
+        at += cnt[s];
+      }
+    }
+    carry += all;
+  }
+  if (rank == 0 && tid == 0) {
+    im.hdr->num_rendered = carry;
+    im.hdr->overflow = carry > cap ? 1u : 0u;
+  }
+  // launch order of the one-CTA-per-tile kernels: see k_tile_scan
+  if (longest_first == 0) {  // raster order
+    for (int t0 = 0; t0 < T; t0 += ROUND) {
+      const int t = t0 + (int)rank * SCAN_CL_THREADS + tid;
+      if (t < T) im.tile_order[t] = (uint32_t)t;
+    }
+    cluster.sync();  // a CTA must not exit while another one may still read its round total
+    return;
+  }
+  if (tid < 64) cls_count[tid] = 0;
+  __syncthreads();  // also makes this CTA's tile_range writes visible to itself
+  auto size_class = [&](int t) {
+    const uint2 r = im.tile_range[t];
+    return 63u - min(63u, (r.y - r.x) >> 6);  // class 0: >= 4032 instances ... class 63: < 64 (incl. empty)
+  };
+  // one shared-memory atomic per (warp, class): lanes of the same class elect a leader
+  auto claim = [&](unsigned* counters, unsigned cls, bool active) -> unsigned {
+    const unsigned peers = __match_any_sync(FULL, active ? cls : 0xffffffffu);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (active && lane == leader) base = atomicAdd(&counters[cls], (unsigned)__popc(peers));
+    base = __shfl_sync(FULL, base, leader);
+    return base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+  };
+  for (int t0 = 0; t0 < T; t0 += ROUND) {
+    const int t = t0 + (int)rank * SCAN_CL_THREADS + tid;
+    claim(cls_count, t < T ? size_class(t) : 0u, t < T);
+  }
+  cluster.sync();  // every CTA's class histogram is complete
+  if (tid < 64) {
+    unsigned tot = 0, mine = 0;
+#pragma unroll
+    for (unsigned r = 0; r < (unsigned)SCAN_CLUSTER; r++) {
+      const unsigned v = *cluster.map_shared_rank(&cls_count[tid], r);
+      mine += r < rank ? v : 0u;
+      tot += v;
+    }
+    // exclusive prefix of the cluster-wide class totals over the 64 classes (two warps)
+    unsigned incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+    if (tid == 31) warp_sums[0] = incl;
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    cls_start[tid] = (tid >= 32 ? warp_sums[0] : 0u) + (incl - tot) + mine;
+  }
+  cluster.sync();  // the remote histograms have been read (a CTA may exit), and cls_start is visible to this CTA
+  for (int t0 = 0; t0 < T; t0 += ROUND) {
+    const int t = t0 + (int)rank * SCAN_CL_THREADS + tid;
+    const unsigned pos = claim(cls_start, t < T ? size_class(t) : 0u, t < T);
+    if (t < T) im.tile_order[longest_first == 2 ? (unsigned)T - 1u - pos : pos] = (uint32_t)t;  // 2: shortest first
   }
 }
 
@@ -416,8 +541,14 @@ static int tile_order_mode() {  // 0 raster, 1 longest first (default), 2 shorte
   const int m = g_tile_order.load();
   return m >= 0 ? m : dflt;
 }
+// GSR_SCAN_CLUSTER=0 (read once per process): the single-CTA scan instead of the 8-CTA cluster form
+static bool scan_cluster() {
+  static const bool v = [] { const char* e = getenv("GSR_SCAN_CLUSTER"); return !(e && e[0] == '0'); }();
+  return v;
+}
 void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
-  launch_high_priority(k_tile_scan, dim3(1), dim3(SCAN_THREADS), 0, st, im, T, tile_order_mode());
+  if (scan_cluster()) launch_high_priority(k_tile_scan_cluster, dim3(SCAN_CLUSTER), dim3(SCAN_CL_THREADS), 0, st, im, T, tile_order_mode());
+  else launch_high_priority(k_tile_scan, dim3(1), dim3(SCAN_THREADS), 0, st, im, T, tile_order_mode());
 }
 
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {
@@ -442,6 +573,10 @@ void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t s
   }
   launch_high_priority(tiny, dim3(T), dim3(SORT_THREADS_TINY), smem_tiny, st, g, im, b);
   launch_high_priority(small, dim3(T), dim3(SORT_THREADS), smem_small, st, g, im, b);
+  // MEASUREMENT ONLY (GSR_SKIP_CROWDED=1): what the two crowded-tier launches cost a view that has no crowded tile --
+  // with it set, tiles beyond SORT_CAP_SMALL entries stay unsorted (wrong results for such views)
+  static const bool skip_crowded = [] { const char* e = getenv("GSR_SKIP_CROWDED"); return e && e[0] == '1'; }();
+  if (skip_crowded) return;
   launch_high_priority(mid, dim3(2 * di.sm_count), dim3(SORT_THREADS), smem_mid, st, g, im, b);  // two CTAs per SM draw the 6k-12k tiles
   launch_high_priority(big, dim3(di.sm_count), dim3(SORT_THREADS), smem_big, st, g, im, b);      // one CTA per SM draws the rest
 }

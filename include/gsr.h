@@ -49,7 +49,12 @@ size_t gsr_binning_bytes(int64_t num_rendered);
  *                      *r_host (if given) receives the true count so the caller can detect it
  *                      (num_rendered > r_capacity) and re-run.
  *   r_host     : optional PINNED host int64 that asynchronously receives num_rendered (either mode).
- * Returns num_rendered (exact mode), r_capacity (pipelined mode), or < 0 on error. */
+ * Returns num_rendered (exact mode), r_capacity (pipelined mode), or < 0 on error.
+ * Exact mode speculates (gsr_set_speculation): from the second view of a (device, P, width, height) on, the binning
+ * buffer is sized for 1.25 x the previous view's count and the rest of the forward is enqueued BEFORE the host blocks
+ * on the count, so the GPU does not idle across the read; a view that needs more is re-binned with its exact count
+ * before the call returns.  Same results and the same returned value either way; `binning_alloc` may then be called
+ * twice in one forward (the last pointer is the one to keep, as with the reference's resize closure). */
 int64_t gsr_forward(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_alloc_fn binning_alloc,
                     void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
                     const float* background, int width, int height, const float* means3D, const float* shs,
@@ -215,6 +220,12 @@ int gsr_debug_export(int P, int width, int height, int64_t R, const char* geom_b
  * long tail of crowded tiles overlaps the next kernel), 2 = shortest first.  Process-wide; returns the previous mode;
  * mode < 0 restores the default (or the GSR_TILE_ORDER environment variable).  Results never depend on it. */
 int gsr_set_tile_order(int mode);
+
+/* Exact-mode speculation of gsr_forward (see there): 1 = on (default; GSR_SPECULATE=0 in the environment turns the
+ * default off), 0 = always the plain blocking read (what `debug` uses), < 0 = back to the default.  Process-wide;
+ * returns the previous setting (-1 = default).  gsr_speculation_stats: forwards whose guess held / that had to re-bin. */
+int gsr_set_speculation(int on);
+int gsr_speculation_stats(int64_t* hits, int64_t* redos);
 
 /* Optional per-stage device timing (CUDA events recorded on the caller's stream around each kernel).
  * Stages: 0 preprocess_fwd, 1 tile_scan, 2 scatter, 3 tile_sort, 4 render_fwd, 5 render_bwd,

@@ -397,3 +397,76 @@ def test_tile_order_never_changes_results():
             assert torch.equal(a, b), mode
         for a, b in zip(res[1][1], res[mode][1]):
             assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12, mode  # float reductions: order only
+
+
+def _fwd_bwd_outputs(r, cam, model, w):
+    for p in model.parameters_list():
+        p.grad = None
+    out = r.render(cam, model)
+    ((out["render"] * w).sum() + out["rendered_depth"].sum() + out["rendered_final_opacity"].sum()).backward()
+    keys = ("render", "rendered_depth", "rendered_median_depth", "rendered_median_weight", "rendered_median_id",
+            "rendered_final_opacity", "radii")
+    return [out[k].detach().clone() for k in keys], [p.grad.clone() for p in model.parameters_list()]
+
+
+def test_exact_mode_speculation_is_invisible():
+    """Exact-mode forwards size the binning buffer from the previous view's count and block on the count only after the
+    whole forward is enqueued (gsr_set_speculation).  Guess large enough (hit) or too small (re-binned with the exact
+    count before the call returns): outputs, num_rendered and the sorted list are those of the plain blocking form."""
+    from gaustudio_b200 import _C, renderers
+    from gaustudio_b200.camera import look_at_camera
+    from gaustudio_b200.synthetic import build_config
+    model, cams, c = build_config("cfg2", P=40000, W=320, H=240, K=2)
+    dev = torch.device("cuda")
+    model.to(dev).requires_grad_(True)
+    near = cams[0].to(dev)
+    # a camera at twice the distance whose target is far off to the side: the ball is mostly outside its frustum, so it
+    # bins a small fraction of the near view's tile instances
+    el = math.radians(c["elev"])
+    pos = (2.0 * c["radius"] * math.cos(el), 0.0, 2.0 * c["radius"] * math.sin(el))
+    far = look_at_camera(pos, (0.0, 1.1 * c["radius"], 0.0), 320, 240, c["fovx"], c["fovy"]).to(dev)
+    r = renderers.make({"name": "vanilla_renderer"})
+    w = torch.randn(3, 240, 320, generator=torch.Generator().manual_seed(5)).to(dev)
+    prev = _C.set_speculation(False)
+    try:
+        plain_far = _fwd_bwd_outputs(r, far, model, w)
+        n_far = _C.last_num_binned()
+        plain_near = _fwd_bwd_outputs(r, near, model, w)
+        n_near = _C.last_num_binned()
+        assert n_near > n_far + n_far // 4 + 4096, (n_far, n_near)  # the near view overflows a guess made from the far one
+        e = torch.Tensor([]).to(dev)
+
+        def raw(cam):  # the binding itself: num_rendered + the sorted list through the debug export
+            out = _C.rasterize_gaussians(
+                torch.zeros(3, device=dev), model.get_attribute("xyz"), e, model.get_attribute("opacity"),
+                model.get_attribute("scale"), model.get_attribute("rot"), 1.0, e, cam.world_view_transform,
+                cam.full_proj_transform, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), 240, 320,
+                model.get_features.contiguous(), 3, cam.camera_center, False, False)
+            ex = _C.debug_export(40000, 320, 240, out[0], out[6], out[7], out[8])
+            return out[0], ex["num_binned"], ex["point_list"][:ex["num_binned"]].clone(), ex["ranges"].clone()
+        with torch.no_grad():
+            raw_plain = {k: raw(cm) for k, cm in (("far", far), ("near", near))}
+
+        _C.set_speculation(True)
+        h0, r0 = _C.speculation_stats()
+        spec_far = _fwd_bwd_outputs(r, far, model, w)       # guess from the near view: far too large -> hit
+        h1, r1 = _C.speculation_stats()
+        assert (h1 - h0, r1 - r0) == (1, 0) and _C.last_num_binned() == n_far
+        spec_near = _fwd_bwd_outputs(r, near, model, w)     # guess from the far view: too small -> re-binned
+        h2, r2 = _C.speculation_stats()
+        assert (h2 - h1, r2 - r1) == (0, 1) and _C.last_num_binned() == n_near
+        spec_near2 = _fwd_bwd_outputs(r, near, model, w)    # guess from the same view -> hit
+        h3, r3 = _C.speculation_stats()
+        assert (h3 - h2, r3 - r2) == (1, 0)
+        with torch.no_grad():
+            raw_spec_far = raw(far)      # hit (guess from the near view)
+            raw_spec_near = raw(near)    # re-binned
+    finally:
+        _C.set_speculation(prev)
+    for plain, spec in ((plain_far, spec_far), (plain_near, spec_near), (plain_near, spec_near2)):
+        for a, b in zip(plain[0], spec[0]):
+            assert torch.equal(a, b)
+        for a, b in zip(plain[1], spec[1]):
+            assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12  # float reductions: order only
+    for a, b in ((raw_plain["far"], raw_spec_far), (raw_plain["near"], raw_spec_near)):
+        assert a[0] == b[0] and a[1] == b[1] and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
