@@ -78,19 +78,6 @@ int high_priority() {
   return prio;
 }
 
-void apply_carveout(const void* kernel) {
-  static const int pref = [] { const char* e = getenv("GSR_CARVEOUT"); return (e && *e) ? atoi(e) : -1; }();
-  if (pref < 0) return;
-  static std::mutex mu;
-  static std::vector<std::pair<int, const void*>> seen;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> l(mu);
-  for (auto& s : seen) if (s.first == dev && s.second == kernel) return;
-  seen.emplace_back(dev, kernel);
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pref > 100 ? 100 : pref) != cudaSuccess) cudaGetLastError();
-}
-
 const DeviceInfo& device_info() {
   static DeviceInfo info[64];
   static std::mutex mu;

@@ -573,10 +573,6 @@ void launch_tile_sort(int T, GeomView g, ImageView im, BinView b, cudaStream_t s
   }
   launch_high_priority(tiny, dim3(T), dim3(SORT_THREADS_TINY), smem_tiny, st, g, im, b);
   launch_high_priority(small, dim3(T), dim3(SORT_THREADS), smem_small, st, g, im, b);
-  // MEASUREMENT ONLY (GSR_SKIP_CROWDED=1): what the two crowded-tier launches cost a view that has no crowded tile --
-  // with it set, tiles beyond SORT_CAP_SMALL entries stay unsorted (wrong results for such views)
-  static const bool skip_crowded = [] { const char* e = getenv("GSR_SKIP_CROWDED"); return e && e[0] == '1'; }();
-  if (skip_crowded) return;
   launch_high_priority(mid, dim3(2 * di.sm_count), dim3(SORT_THREADS), smem_mid, st, g, im, b);  // two CTAs per SM draw the 6k-12k tiles
   launch_high_priority(big, dim3(di.sm_count), dim3(SORT_THREADS), smem_big, st, g, im, b);      // one CTA per SM draws the rest
 }

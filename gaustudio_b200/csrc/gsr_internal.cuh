@@ -72,14 +72,9 @@ struct BinView {               // point_list comes FIRST: its address does not d
 // the two kinds of work never overlap.  With the high priority its CTAs take the slots that free up first.
 // GSR_PRIORITY=0 (read once) launches everything at the default priority.
 int high_priority();  // the device's greatest stream priority, or 0 (= default) when disabled (gsr_api.cu)
-// Experiment knob GSR_CARVEOUT=<0..100> (read once): every kernel of the library asks for the same shared-memory
-// carveout (cudaFuncAttributePreferredSharedMemoryCarveout) instead of the driver's per-kernel choice -- kernels of
-// different views that want different L1 / shared-memory splits cannot share an SM.  Unset: the driver chooses.
-void apply_carveout(const void* kernel);  // gsr_api.cu; a no-op unless the knob is set
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_high_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                         Args&&... args) {
-  apply_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -556,7 +556,6 @@ static size_t render_pad() {
   return v;
 }
 template <typename K> static void allow_pad(K kernel) {
-  apply_carveout(reinterpret_cast<const void*>(kernel));
   if (render_pad()) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_pad());
 }
 

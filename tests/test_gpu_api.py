@@ -251,18 +251,34 @@ def test_fused_path_with_mostly_culled_ctas_matches_unfused():
     from gaustudio_b200 import renderers
     from gaustudio_b200.synthetic import build_config
     dev = torch.device("cuda")
-    imgs = {}
-    for fused in (False, True):
-        model, cams, _ = build_config("cfg5", P=40000, K=1, W=240, H=180)
-        model.to(dev)
-        r = renderers.make({"name": "vanilla_renderer", "fused_activations": fused})
-        with torch.no_grad():
-            out = r.render(cams[0].to(dev), model)
-        imgs[fused] = [out[k].cpu().numpy() for k in ("render", "rendered_depth", "rendered_final_opacity")]
-        vis = (out["radii"] > 0).float().mean().item()
-        assert 0.05 < vis < 0.7, vis
-    for a, b in zip(imgs[True], imgs[False]):
-        U.assert_images_close(a, b, atol=1e-4, outlier_frac=1e-3, what="fused image, sparse CTAs")
+    keys = ("render", "rendered_depth", "rendered_final_opacity")
+
+    def render_both():
+        imgs = {}
+        for fused in (False, True):
+            model, cams, _ = build_config("cfg5", P=40000, K=1, W=240, H=180)
+            model.to(dev)
+            r = renderers.make({"name": "vanilla_renderer", "fused_activations": fused})
+            with torch.no_grad():
+                out = r.render(cams[0].to(dev), model)
+            imgs[fused] = [out[k].cpu().numpy() for k in keys]
+            vis = (out["radii"] > 0).float().mean().item()
+            assert 0.05 < vis < 0.7, vis
+        return imgs
+    imgs = render_both()
+    try:
+        for a, b in zip(imgs[True], imgs[False]):
+            U.assert_images_close(a, b, atol=1e-4, outlier_frac=1e-3, what="fused image, sparse CTAs")
+    except AssertionError as ex:
+        # the forward is deterministic: say which of the two renders does not reproduce, and where
+        again = render_both()
+        stable = {f: all(np.array_equal(x, y) for x, y in zip(imgs[f], again[f])) for f in (False, True)}
+        d = np.abs(imgs[True][0] - imgs[False][0]).max(axis=0)
+        pad = np.zeros((192, 240), np.float32); pad[:180] = d
+        per_tile = pad.reshape(12, 16, 15, 16).max(axis=(1, 3))
+        worst = np.argsort(per_tile.ravel())[::-1][:8]
+        raise AssertionError(f"{ex}; re-render reproduces: unfused {stable[False]}, fused {stable[True]}; tiles over 1e-4: "
+                             f"{int((per_tile > 1e-4).sum())}/180, worst {[(int(t), float(per_tile.ravel()[t])) for t in worst]}")
 
 
 def test_views_on_concurrent_streams_match_sequential():

@@ -47,7 +47,7 @@ for r in rows[2:]:
 open(os.path.join(out, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
 grp = {"preprocess_fwd": traffic.get("k_preprocess_fwd"), "render_fwd": traffic.get("k_render_fwd"), "render_bwd": traffic.get("k_render_bwd"),
        "preprocess_bwd": traffic.get("k_preprocess_bwd"),
-       "binning": sum(v for k, v in traffic.items() if k in ("k_tile_scan", "k_scatter", "k_tile_sort")) or None}
+       "binning": sum(v for k, v in traffic.items() if k.startswith(("k_tile_scan", "k_scatter", "k_tile_sort"))) or None}
 # merge into the committed file (bench.py reads it) only when the capture holds all five stages of a view;
 # a partial capture (e.g. tools/profile_aux.py) must not drop the stages it did not see
 tf = os.path.join(out, "ncu_traffic.json")
