@@ -21,8 +21,13 @@
 #include "gsr_internal.cuh"
 #include <atomic>
 #include <cstdlib>
+#ifndef GSR_WITH_CLUSTER_SCAN
+#define GSR_WITH_CLUSTER_SCAN 0
+#endif
+#if GSR_WITH_CLUSTER_SCAN
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
+#endif
 
 
 namespace gsr {
@@ -132,13 +137,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(ImageView im, int T,
   }
 }
 
-// ---- level 1a, cluster form (default): the same scan by a thread-block cluster of 8 CTAs ---------------------------
+#if GSR_WITH_CLUSTER_SCAN
+// ---- level 1a, cluster form: the same scan by a thread-block cluster of 8 CTAs -- EXPERIMENTAL, not in the default build
+// Compiled only with -DGSR_WITH_CLUSTER_SCAN=1 (tools/build_variants.py cluster_scan) and then selected at run time with
+// GSR_SCAN_CLUSTER=1.  It is 2.5x faster than the single-CTA scan (0.015 vs 0.037 ms at 1080p) and passed the whole GPU
+// suite, but with it the first un-fused render of tests/test_gpu_api.py::test_fused_path_with_mostly_culled_ctas_...
+// came out slightly different (a few 1e-3 on ~140 of 180 tiles, not reproducible on re-render) in 4 of 33 fresh-process
+// runs, against 0 of 29 with the single-CTA scan (profiles/r2c_flake_arms.md); the cause was not found in the GPU time
+// that was left, so the validated single-CTA kernel stays the product path.
 // The single-CTA scan is pure latency on one SM (37 us at 1080p: 8160 tiles x 16 counters through one SM's load path,
 // twice, plus a counting sort with contended shared-memory atomics).  Here every thread owns ONE tile per round (a round
 // = 8 x 1024 tiles: a 1080p image is one round), its 16 counters stay in registers between the total and the cursor
 // pass, the 8 CTAs exchange their round totals through distributed shared memory (one cluster barrier per round), and
 // the size-class counting sort of the launch order uses warp-aggregated atomics and a cluster-wide class histogram.
-// Same outputs as k_tile_scan except for the (free) order of tiles inside a size class and of the crowded-tile list.
+// Intended outputs: those of k_tile_scan except for the (free) order of tiles inside a size class and of the crowded-tile list.
 constexpr int SCAN_CLUSTER = 8;
 #ifndef GSR_SCAN_CL_THREADS
 #define GSR_SCAN_CL_THREADS 512
@@ -254,6 +266,7 @@ k_tile_scan_cluster(ImageView im, int T, int longest_first) {
     if (t < T) im.tile_order[longest_first == 2 ? (unsigned)T - 1u - pos : pos] = (uint32_t)t;  // 2: shortest first
   }
 }
+#endif  // GSR_WITH_CLUSTER_SCAN
 
 // ---- level 1b: scatter one entry per (Gaussian, touched tile) ------------------------------------
 #ifndef GSR_SCATTER_THREADS
@@ -541,14 +554,16 @@ static int tile_order_mode() {  // 0 raster, 1 longest first (default), 2 shorte
   const int m = g_tile_order.load();
   return m >= 0 ? m : dflt;
 }
-// GSR_SCAN_CLUSTER=0 (read once per process): the single-CTA scan instead of the 8-CTA cluster form
-static bool scan_cluster() {
-  static const bool v = [] { const char* e = getenv("GSR_SCAN_CLUSTER"); return !(e && e[0] == '0'); }();
-  return v;
-}
 void launch_tile_scan(ImageView im, int T, cudaStream_t st) {
-  if (scan_cluster()) launch_high_priority(k_tile_scan_cluster, dim3(SCAN_CLUSTER), dim3(SCAN_CL_THREADS), 0, st, im, T, tile_order_mode());
-  else launch_high_priority(k_tile_scan, dim3(1), dim3(SCAN_THREADS), 0, st, im, T, tile_order_mode());
+#if GSR_WITH_CLUSTER_SCAN
+  // experimental builds only: GSR_SCAN_CLUSTER=1 (read once per process) selects the 8-CTA cluster form
+  static const bool cluster = [] { const char* e = getenv("GSR_SCAN_CLUSTER"); return e && e[0] == '1'; }();
+  if (cluster) {
+    launch_high_priority(k_tile_scan_cluster, dim3(SCAN_CLUSTER), dim3(SCAN_CL_THREADS), 0, st, im, T, tile_order_mode());
+    return;
+  }
+#endif
+  launch_high_priority(k_tile_scan, dim3(1), dim3(SCAN_THREADS), 0, st, im, T, tile_order_mode());
 }
 
 void launch_scatter(int P, int gx, int T, GeomView g, ImageView im, BinView b, cudaStream_t st) {

@@ -20,6 +20,9 @@ VARIANTS = {
     "tinycap4096": ["-DGSR_SORT_CAP_TINY=4096"],
     "tinycap4096_256": ["-DGSR_SORT_CAP_TINY=4096", "-DGSR_SORT_THREADS_TINY=256"],
     "tinycap1536": ["-DGSR_SORT_CAP_TINY=1536"],
+    # experimental 8-CTA cluster tile scan compiled in (then GSR_SCAN_CLUSTER=1 selects it at run time)
+    "cluster_scan": ["-DGSR_WITH_CLUSTER_SCAN=1"],
+    "cluster_scan1024": ["-DGSR_WITH_CLUSTER_SCAN=1", "-DGSR_SCAN_CL_THREADS=1024"],
 }
 
 

@@ -1,7 +1,8 @@
 #!/bin/bash
 # End-of-round evidence run (1 x B200), most important first: GPU test suite, both bench arms, cfg5, training step, the
 # launch list of bench.py, ncu --set full of one steady-state step, then a repeat loop of the binding tests and the same
-# suite / benches with the two late-round-2 switches off (GSR_SCAN_CLUSTER=0 GSR_SPECULATE=0) for comparison.
+# suite / benches with the exact-mode speculation off (GSR_SPECULATE=0) for comparison.  (The r2c capture in profiles/
+# was taken when the experimental cluster scan was still a run-time default: its `off` leg also had GSR_SCAN_CLUSTER=0.)
 # Numbers printed under ncu are never quoted.  usage: final_capture.sh [tag]
 TAG=${1:-r2c}
 O=gpurun_out
@@ -22,7 +23,7 @@ for i in 1 2 3 4 5 6; do
   echo "loop $i: $(tail -1 $O/${TAG}_loop_$i.txt)"; grep -h "AssertionError: fused" $O/${TAG}_loop_$i.txt | head -2
 done; lap "loop"
 timeout -k 10 400 ncu --set full --clock-control none --import-source on -k regex:k_ -s 24 -c 12 -f -o $O/${TAG}_prof python tools/profile_one.py cfg3 4 > $O/${TAG}_prof.log 2>&1; lap "ncu full $?"
-export GSR_SCAN_CLUSTER=0 GSR_SPECULATE=0
+export GSR_SPECULATE=0
 timeout -k 10 300 python -m pytest tests -m gpu -q > $O/${TAG}_off_pytest_gpu.txt 2>&1; lap "pytest (switches off) exit $? : $(tail -1 $O/${TAG}_off_pytest_gpu.txt)"
 timeout -k 10 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/${TAG}_off_bench_new.json 2> $O/${TAG}_off_bench_new.err; lap "bench new (off) $?"
 timeout -k 10 200 python bench.py --config cfg5 --steps 20 --warmup 5 --no-cpu-baseline > $O/${TAG}_off_bench_cfg5.json 2> $O/${TAG}_off_bench_cfg5.err; lap "cfg5 (off) $?"
