@@ -277,8 +277,11 @@ def test_fused_path_with_mostly_culled_ctas_matches_unfused():
         pad = np.zeros((192, 240), np.float32); pad[:180] = d
         per_tile = pad.reshape(12, 16, 15, 16).max(axis=(1, 3))
         worst = np.argsort(per_tile.ravel())[::-1][:8]
+        # colour only (SH inputs) or geometry as well (depth / opacity move too)?  first render vs its own re-render
+        moved = {f: [float(np.abs(x - y).max()) for x, y in zip(imgs[f], again[f])] for f in (False, True)}
         raise AssertionError(f"{ex}; re-render reproduces: unfused {stable[False]}, fused {stable[True]}; tiles over 1e-4: "
-                             f"{int((per_tile > 1e-4).sum())}/180, worst {[(int(t), float(per_tile.ravel()[t])) for t in worst]}")
+                             f"{int((per_tile > 1e-4).sum())}/180, worst {[(int(t), float(per_tile.ravel()[t])) for t in worst]}; "
+                             f"max |first - re-render| of (colour, depth, opacity): unfused {moved[False]}, fused {moved[True]}")
 
 
 def test_views_on_concurrent_streams_match_sequential():
