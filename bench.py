@@ -718,9 +718,11 @@ def run_dropin(a, _C, model, hcams, dev, renderers, step, K, Wn):
         _C.restore_pipeline(saved)
     return {"value": K / (ms_dev * 1e-3), "unit": "views/s", "ms_per_step": ms_dev / K,
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e / K},
-            "host_enqueue_ms_per_step": round(host_ms, 4),
-            "mode": "fused_activations=False, exact forward, 1 stream, eager launches (--fused 0 --streams 1 --graph 0 "
-                    "--pipelined 0): what gaustudio/renderers/base.py:10-63 sees"}
+            "host_enqueue_ms_per_step": round(host_ms, 4),  # includes the time the host is blocked on the count read
+            "speculation": dict(zip(("hits", "rebinned"), _C.speculation_stats())),
+            "mode": "fused_activations=False, exact forward (its blocking count read behind the enqueued forward: capacity "
+                    "guessed from the previous view, re-binned if too small), 1 stream, eager launches (--fused 0 "
+                    "--streams 1 --graph 0 --pipelined 0): what gaustudio/renderers/base.py:10-63 sees"}
 
 
 def run_train(a, _C, L, parallel, model, hcams, c, nviews_total, step, renderer, loss_fn, normal, rank, world, dev, sync_all):

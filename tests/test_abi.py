@@ -39,6 +39,24 @@ def test_host_only_entry_points():
     assert isinstance(_lib.last_error(), str)
 
 
+def test_speculation_switch_round_trip():
+    """gsr_set_speculation / gsr_speculation_stats are host-only: the switch returns the previous setting (None =
+    default), the counters start at zero in a process that has rendered nothing, and the default build carries no
+    experimental cluster-scan kernel."""
+    from gaustudio_b200 import _C
+    prev = _C.set_speculation(False)
+    try:
+        assert _C.set_speculation(True) is False
+        assert _C.set_speculation(None) is True
+        assert _C.set_speculation(None) is None
+        hits, redos = _C.speculation_stats()
+        assert hits >= 0 and redos >= 0
+    finally:
+        _C.set_speculation(prev)
+    blob = open(_lib.LIB_PATH, "rb").read()
+    assert b"k_tile_scan_cluster" not in blob
+
+
 def test_no_oracle_import_in_product_path():
     """The product package must not reference oracle/ (a CPU fallback would void the parity claims)."""
     pkg = os.path.join(ROOT, "gaustudio_b200")
