@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: since the end of round 2 the cluster tile scan is compiled only into the `cluster_scan` variant (python tools/build_variants.py
+# cluster_scan; run with GSR_LIB=gaustudio_b200/variants/libgsr_cluster_scan.so): with the default library GSR_SCAN_CLUSTER is ignored.
 # failure rate of the sparse fused/un-fused test (in its test-file sequence, fresh process each) per switch setting;
 # four processes at a time
 mkdir -p gpurun_out/arms

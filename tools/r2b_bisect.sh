@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: since the end of round 2 the cluster tile scan is compiled only into the `cluster_scan` variant (python tools/build_variants.py
+# cluster_scan; run with GSR_LIB=gaustudio_b200/variants/libgsr_cluster_scan.so): with the default library GSR_SCAN_CLUSTER is ignored.
 # which of the two late changes breaks test_fused_path_with_mostly_culled_ctas_matches_unfused?
 mkdir -p gpurun_out
 T=tests/test_gpu_api.py::test_fused_path_with_mostly_culled_ctas_matches_unfused
